@@ -1,0 +1,252 @@
+"""Shared machinery of bear_net / bear_ref: flat parameter + gradient buffers, the per-step
+allreduce, Keras-style optimizers, and the routing of AR heads onto the fused kernels.
+
+Data parallelism (replaces tf.distribute.MirroredStrategy, bear_net.py:246,273,290-291): one process
+per GPU, k-mer rows sharded by ``KmerDataset.shard``; per optimizer step ONE allreduce(SUM) of the
+flat float64 buffer ``[loss, d h_signed, d params...]`` (<= 52 KB), then the identical update on
+every rank.  Evaluation accumulates locally and allreduces its handful of scalars once at the end.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib, core
+from ._lib import lib, check, ptr
+from .ar_funcs import ARFunc
+from .dataloader import KmerDataset
+
+EXPLICIT_CHUNK = 1 << 18      # rows per one-hot materialisation for explicit (torch-op) heads
+
+
+def world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def allreduce_sum(t):
+    if world()[1] > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
+def head_kind(ar_func):
+    return getattr(ar_func, 'kind', 'custom') if ar_func is not None else 'none'
+
+
+def fused_linear_ok(ar_func, table):
+    return head_kind(ar_func) == 'linear' and table.alphabet in ('dna', 'rna')
+
+
+class FlatParams:
+    """[h_signed, params...] packed in one contiguous float64 device buffer.  The tensors handed to
+    the user (and captured by plugin closures) are re-pointed to views of it, so the optimizer
+    kernel and the allreduce see a single buffer while ``ar_func`` keeps working unchanged."""
+
+    def __init__(self, tensors):
+        dev = _lib.device()
+        self.tensors = list(tensors)
+        self.sizes = [int(t.numel()) for t in self.tensors]
+        self.total = sum(self.sizes)
+        self.flat = torch.zeros(self.total, dtype=torch.float64, device=dev)
+        self.offsets = []
+        o = 0
+        for t, n in zip(self.tensors, self.sizes):
+            view = self.flat[o:o + n].view(t.shape)
+            view.copy_(t.detach().to(dev, torch.float64))
+            t.data = view
+            self.offsets.append(o)
+            o += n
+        # gradient buffer: [loss, d params...]
+        self.grad = torch.zeros(1 + self.total, dtype=torch.float64, device=dev)
+
+    def grad_view(self, i):
+        o = 1 + self.offsets[i]
+        return self.grad[o:o + self.sizes[i]].view(self.tensors[i].shape)
+
+
+class Optimizer:
+    """tf.keras.optimizers.<name>(learning_rate) with Keras (OptimizerV2) defaults, on the flat buffer
+    (bear_net.py:264-265).  Adam runs as one libbear_b200 kernel; the others are a few torch ops."""
+
+    def __init__(self, name, learning_rate, n, device):
+        self.name, self.lr = name, float(learning_rate)
+        z = lambda: torch.zeros(n, dtype=torch.float64, device=device)
+        if name == 'Adam':
+            self.m, self.v = z(), z()
+            self.step = torch.zeros(1, dtype=torch.int64, device=device)
+        elif name == 'SGD':
+            pass
+        elif name == 'RMSprop':
+            self.v = z()
+        elif name == 'Adagrad':
+            self.v = z() + 0.1
+        else:
+            raise ValueError("optimizer '%s' is not supported (Adam, SGD, RMSprop, Adagrad)" % name)
+
+    def apply(self, params, grads):
+        if self.name == 'Adam':
+            check(lib.bear_adam_update(ptr(params), ptr(grads), ptr(self.m), ptr(self.v), params.numel(),
+                                       self.lr, 0.9, 0.999, 1e-7, ptr(self.step), _lib.stream()))
+        elif self.name == 'SGD':
+            params.sub_(self.lr * grads)
+        elif self.name == 'RMSprop':
+            self.v.mul_(0.9).addcmul_(grads, grads, value=0.1)
+            params.sub_(self.lr * grads / (self.v.sqrt() + 1e-7))
+        elif self.name == 'Adagrad':
+            self.v.addcmul_(grads, grads)
+            params.sub_(self.lr * grads / (self.v.sqrt() + 1e-7))
+
+
+def workspace(table, nparams=0):
+    return torch.empty(lib.bear_workspace_doubles(table.num_rows, table.lag, nparams), dtype=torch.float64,
+                       device=_lib.device())
+
+
+def onehot_rows(table, r0, n):
+    """core.tf_one_hot of rows [r0, r0+n) from the packed codes, on the device."""
+    k, _ = table.device_tensors()
+    out = torch.empty((n, table.lag, table.A1), dtype=torch.float64, device=k.device)
+    check(lib.bear_decode_onehot(ptr(k[r0:r0 + n]), n, table.lag, _lib.ALPHABET_IDS[table.alphabet], ptr(out),
+                                 _lib.stream()))
+    return out
+
+
+def check_dataset(data):
+    if not isinstance(data, KmerDataset):
+        raise TypeError('data must be a KmerDataset from bear_b200.dataloader (dataloader / sparse_dataloader)')
+    if data.map_fn is not None:
+        raise TypeError('train / evaluation take the un-mapped KmerDataset; column selection happens on the device')
+    return data.table
+
+
+# ---------------------------------------------------------------------------------------------
+# training
+# ---------------------------------------------------------------------------------------------
+def train_loop(data, num_kmers, ds_loc, train_ar, acc_steps, fp, optimizer_name, learning_rate, step_fn,
+               writer=None, loss_save=None):
+    """The loop of bear_net.train (bear_net.py:293-315): ``step_fn(r0, n, scale)`` adds the loss and
+    gradients of one batch into ``fp.grad``; every ``acc_steps`` batches the buffer is allreduced,
+    the loss recorded and the optimizer applied."""
+    opt = Optimizer(optimizer_name, learning_rate, fp.total, fp.flat.device)
+    fp.grad.zero_()
+    losses = []
+    step = 1
+    for r0, n, gB in data.batches():
+        step_fn(r0, n, float(num_kmers) / float(gB))
+        if step % acc_steps == 0:
+            allreduce_sum(fp.grad)
+            if writer is not None or loss_save is not None:
+                losses.append((step, (-fp.grad[0] / acc_steps).clone()))
+            opt.apply(fp.flat, fp.grad[1:])
+            fp.grad.zero_()
+        step += 1
+    if losses:
+        vals = torch.stack([v for _, v in losses]).cpu().tolist()     # one D2H copy at the end
+        for (s, _), v in zip(losses, vals):
+            if loss_save is not None:
+                loss_save.append(v)
+            if writer is not None and hasattr(writer, 'add_scalar'):
+                writer.add_scalar('elbo', v, s)
+
+
+def explicit_f(ar_func, table, r0, n, extra=None):
+    """f = ar_func(onehot) (and for bear_ref heads, of the reference counts) for rows [r0, r0+n)."""
+    oh = onehot_rows(table, r0, n)
+    f = ar_func(oh) if extra is None else ar_func(oh, extra)
+    if f.dim() == 1:
+        f = f.expand(n, -1)
+    return f
+
+
+def explicit_train_step(table, ds_loc, r0, n, scale, train_ar, fp, ws, f_fn):
+    """One batch through a caller-evaluated head: chunks of rows -> f (torch autograd) ->
+    bear_dm_train_step_explicit -> backward through the head."""
+    h_signed = fp.tensors[0]
+    for c0 in range(r0, r0 + n, EXPLICIT_CHUNK):
+        cn = min(EXPLICIT_CHUNK, r0 + n - c0)
+        with torch.enable_grad():
+            f = f_fn(c0, cn)
+        fc = f.detach().contiguous()
+        gf = torch.empty_like(fc)
+        check(lib.bear_dm_train_step_explicit(table.col_ptr(ds_loc), table.stride, c0, cn, ptr(fc), ptr(h_signed),
+                                              scale, int(train_ar), ptr(fp.grad), ptr(gf), None, ptr(ws),
+                                              _lib.stream()))
+        if f.requires_grad:
+            f.backward(gf)
+    for i, t in enumerate(fp.tensors):
+        if t.grad is not None:
+            fp.grad_view(i).add_(t.grad)
+            t.grad = None
+
+
+# ---------------------------------------------------------------------------------------------
+# evaluation
+# ---------------------------------------------------------------------------------------------
+def eval_loop(data, ds_loc_train, ds_loc_test, h, van_reg, head, head_ptr_fn, seed):
+    """bear_net.evaluation's accumulation (bear_net.py:439-457) on the packed table.  ``head`` is a
+    BEAR_HEAD_* id; ``head_ptr_fn(r0, n)`` returns (tensor kept alive, explicit row offset) for the
+    head argument of bear_eval_step.  Returns float64 CPU tensors
+    (ll_ear[H], ll_arm, ll_van[V], cor_ear[H], cor_arm, cor_van[V], total_len)."""
+    table = data.table
+    k, c = table.device_tensors()
+    dev = k.device
+    h = torch.as_tensor(np.asarray(h, dtype=np.float64)).reshape(-1)
+    van = torch.as_tensor(np.asarray(van_reg, dtype=np.float64)).reshape(-1)
+    H, V = h.numel(), van.numel()
+    if seed is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    ws = workspace(table)
+    test_ptr = table.col_ptr(ds_loc_test)
+    train_ptr = table.col_ptr(ds_loc_train) if ds_loc_train >= 0 else None
+    M = _lib.MAX_MODELS
+    passes = max(1, -(-H // M), -(-V // M))
+    ll_ear, cor_ear = torch.zeros(H, dtype=torch.float64), torch.zeros(H, dtype=torch.float64)
+    ll_van, cor_van = torch.zeros(V, dtype=torch.float64), torch.zeros(V, dtype=torch.float64)
+    ll_arm = cor_arm = total = None
+    for p in range(passes):
+        hp = h[p * M:(p + 1) * M].to(dev)
+        vp = van[p * M:(p + 1) * M].to(dev)
+        Hp, Vp = hp.numel(), vp.numel()
+        acc = torch.zeros(2 * Hp + 2 * Vp + 3, dtype=torch.float64, device=dev)
+        for r0, n, _ in data.batches():
+            keep, hptr = head_ptr_fn(r0, n)
+            check(lib.bear_eval_step(ptr(k), test_ptr, train_ptr, table.stride, r0, n, table.lag, head, hptr,
+                                     ptr(hp) if Hp else None, Hp, ptr(vp) if Vp else None, Vp, seed, ptr(acc),
+                                     ptr(ws), _lib.stream()))
+            del keep
+        acc = allreduce_sum(acc).cpu()
+        o = 0
+        ll_ear[p * M:p * M + Hp] = acc[o:o + Hp]; o += Hp
+        if p == 0:
+            ll_arm = acc[o].clone()
+        o += 1
+        ll_van[p * M:p * M + Vp] = acc[o:o + Vp]; o += Vp
+        cor_ear[p * M:p * M + Hp] = acc[o:o + Hp]; o += Hp
+        if p == 0:
+            cor_arm = acc[o].clone()
+        o += 1
+        cor_van[p * M:p * M + Vp] = acc[o:o + Vp]; o += Vp
+        if p == 0:
+            total = acc[o].clone()
+    return ll_ear, ll_arm, ll_van, cor_ear, cor_arm, cor_van, total
+
+
+def explicit_head_ptr_fn(f_fn):
+    """Adapter for heads evaluated with torch ops: computes f for the batch and passes it as a
+    BEAR_HEAD_EXPLICIT array whose row 0 is table row r0."""
+    def fn(r0, n):
+        with torch.no_grad():
+            parts = [f_fn(c0, min(EXPLICIT_CHUNK, r0 + n - c0)) for c0 in range(r0, r0 + n, EXPLICIT_CHUNK)]
+            f = (parts[0] if len(parts) == 1 else torch.cat(parts)).contiguous()
+        return f, ptr(f)
+    return fn
+
+
+def finish_evaluation(ll_ear, ll_arm, ll_van, cor_ear, cor_arm, cor_van, total):
+    """bear_net.py:459-463."""
+    return (ll_ear, ll_arm, ll_van,
+            torch.exp(-ll_ear / total), torch.exp(-ll_arm / total), torch.exp(-ll_van / total),
+            cor_ear / total, cor_arm / total, cor_van / total)

@@ -1,0 +1,305 @@
+// Dense (reference-shaped float64 tensor) kernels: unpacking the packed table into the reference's
+// tensors, the generic distributions of core.py, and the posterior sampler of log_gamma.py.
+#include <math.h>
+
+#include "bear_b200.h"
+#include "bear_common.cuh"
+#include "bear_host.h"
+
+namespace {
+
+using namespace bear;
+
+constexpr int THREADS = 256;
+constexpr int MAX_A1 = 32;
+
+inline int blocks_for(int64_t n, int cap = 148 * 16) {
+    int64_t b = (n + THREADS - 1) / THREADS;
+    if (b < 1) b = 1;
+    return int(b < cap ? b : cap);
+}
+
+__device__ __forceinline__ int decode_symbol(uint64_t code, int j, int lag, int alphabet) {
+    if (alphabet == BEAR_ALPHABET_PROT) {
+        const int c = int((code >> (5 * (lag - 1 - j))) & 31u);
+        return c <= 20 ? c : 21;               // 21 = unknown -> all-zero row
+    }
+    const int nstart = int(code >> 58);
+    return j < nstart ? 4 : int((code >> (2 * (lag - 1 - j))) & 3u);
+}
+
+// core.tf_one_hot (core.py:156-174) from packed codes
+__global__ void decode_onehot_kernel(const uint64_t* __restrict__ kmers, int64_t n, int lag, int alphabet, int A1,
+                                     double* __restrict__ out) {
+    const int64_t total = n * lag;
+    for (int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += int64_t(gridDim.x) * blockDim.x) {
+        const int64_t i = idx / lag;
+        const int j = int(idx - i * lag);
+        const int s = decode_symbol(kmers[i], j, lag, alphabet);
+        double* o = out + idx * A1;
+        for (int b = 0; b < A1; ++b) o[b] = (b == s) ? 1.0 : 0.0;
+    }
+}
+
+__global__ void decode_symbols_kernel(const uint64_t* __restrict__ kmers, int64_t n, int lag, int alphabet,
+                                      uint8_t* __restrict__ out) {
+    const int64_t total = n * lag;
+    for (int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += int64_t(gridDim.x) * blockDim.x) {
+        const int64_t i = idx / lag;
+        const int j = int(idx - i * lag);
+        out[idx] = uint8_t(decode_symbol(kmers[i], j, lag, alphabet));
+    }
+}
+
+// group-planar uint32 [G][A1][stride] -> dense float64 [n, G, A1] (the tensor of dataloader.py:44-46)
+__global__ void unpack_counts_kernel(const uint32_t* __restrict__ counts, int64_t stride, int64_t n, int G, int A1,
+                                     double* __restrict__ out) {
+    const int GA = G * A1;
+    const int64_t total = n * GA;
+    for (int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += int64_t(gridDim.x) * blockDim.x) {
+        const int64_t i = idx / GA;
+        const int p = int(idx - i * GA);
+        out[idx] = double(counts[int64_t(p) * stride + i]);
+    }
+}
+
+__device__ __forceinline__ bool is_count(double v) { return v >= 0.0 && v < 9.0e15 && v == floor(v); }
+
+// lgamma(a + v) - lgamma(a): integer fast path when v is a count, else two lgamma calls as in tf.math.lbeta
+__device__ __forceinline__ double lg_diff_real(double a, double v) {
+    if (v == 0.0) return 0.0;
+    if (is_count(v) && a > 0.0) {
+        const LgDg t = lgdg_diff<false>(a, v);
+        return t.add + (t.mul == 1.0 ? 0.0 : log(t.mul));
+    }
+    return lgamma(a + v) - lgamma(a);
+}
+
+__device__ __forceinline__ double dg_diff_real(double a, double v) {
+    if (v == 0.0) return 0.0;
+    if (is_count(v) && a > 0.0) return lgdg_diff<true>(a, v).dg;
+    return digamma_pos(a + v) - digamma_pos(a);
+}
+
+// core.tfpDirichletMultinomialPerm.counts_log_prob (core.py:73-74)
+__global__ void dm_logprob_kernel(const double* __restrict__ conc, int64_t conc_rows, const double* __restrict__ value,
+                                  int64_t n, int A1, double* __restrict__ out) {
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+        const double* a = conc + (i % conc_rows) * A1;
+        const double* v = value + i * A1;
+        double s = 0.0, tot = 0.0, ll = 0.0;
+        for (int b = 0; b < A1; ++b) {
+            s += a[b];
+            tot += v[b];
+            ll += lg_diff_real(a[b], v[b]);
+        }
+        out[i] = ll - lg_diff_real(s, tot);
+    }
+}
+
+__global__ void dm_logprob_bwd_kernel(const double* __restrict__ conc, int64_t conc_rows, const double* __restrict__ value,
+                                      int64_t n, int A1, const double* __restrict__ gout, double* __restrict__ gconc) {
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+        const double* a = conc + (i % conc_rows) * A1;
+        const double* v = value + i * A1;
+        double s = 0.0, tot = 0.0;
+        for (int b = 0; b < A1; ++b) {
+            s += a[b];
+            tot += v[b];
+        }
+        const double dt = dg_diff_real(s, tot);
+        const double go = gout ? gout[i] : 1.0;
+        for (int b = 0; b < A1; ++b) gconc[i * A1 + b] = go * (dg_diff_real(a[b], v[b]) - dt);
+    }
+}
+
+// core.tfpMultinomialPerm.counts_log_prob (core.py:138-139): sum multiply_no_nan(log p, c)
+__global__ void mn_logprob_kernel(const double* __restrict__ probs, int64_t probs_rows, const double* __restrict__ value,
+                                  int64_t n, int A1, double* __restrict__ out) {
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+        const double* p = probs + (i % probs_rows) * A1;
+        const double* v = value + i * A1;
+        double ll = 0.0;
+        for (int b = 0; b < A1; ++b)
+            if (v[b] != 0.0) ll = fma(v[b], log(p[b]), ll);
+        out[i] = ll;
+    }
+}
+
+__global__ void mn_logprob_bwd_kernel(const double* __restrict__ probs, int64_t probs_rows, const double* __restrict__ value,
+                                      int64_t n, int A1, const double* __restrict__ gout, double* __restrict__ gprobs) {
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+        const double* p = probs + (i % probs_rows) * A1;
+        const double* v = value + i * A1;
+        const double go = gout ? gout[i] : 1.0;
+        for (int b = 0; b < A1; ++b) gprobs[i * A1 + b] = v[b] != 0.0 ? go * v[b] / p[b] : 0.0;
+    }
+}
+
+// ml_output (core.py:69-71,134-136)
+__global__ void ml_output_kernel(const double* __restrict__ x, int64_t n, int A1, double sigma, int64_t seed,
+                                 double* __restrict__ out) {
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+        const double* v = x + i * A1;
+        int best = 0;
+        double top = -INFINITY;
+        for (int b = 0; b < A1; ++b) {
+            double t = v[b];
+            if (seed >= 0) t += sigma * rng_normal(uint64_t(seed), uint64_t(i), uint64_t(b));
+            if (t > top) {
+                top = t;
+                best = b;
+            }
+        }
+        out[i] = double(best);
+    }
+}
+
+// log X, X ~ Gamma(a, 1).  a >= 1: Marsaglia-Tsang squeeze; a < 1: log Gamma(a+1) + log(U)/a, which
+// stays finite where X itself underflows (the reason log_gamma.py exists, log_gamma.py:17-31).
+__device__ double loggamma_draw(double a, uint64_t seed, uint64_t stream) {
+    double boost = 0.0;
+    uint64_t ctr = 0;
+    if (a < 1.0) {
+        boost = log(u01(rng_u64(seed, stream, ctr++))) / a;
+        a += 1.0;
+    }
+    const double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+    for (;;) {
+        const double x = rng_normal(seed, stream, ctr++);
+        const double t = 1.0 + c * x;
+        if (t <= 0.0) continue;
+        const double v = t * t * t;
+        const double u = u01(rng_u64(seed, stream, ctr++));
+        const double lv = log(v);
+        if (log(u) < 0.5 * x * x + d - d * v + d * lv) return log(d) + lv + boost;
+    }
+}
+
+__global__ void loggamma_sample_kernel(const double* __restrict__ conc, int64_t n, int64_t n_samples, int64_t seed,
+                                       double* __restrict__ out) {
+    const int64_t total = n * n_samples;
+    for (int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += int64_t(gridDim.x) * blockDim.x) {
+        const int64_t i = idx % n;
+        out[idx] = loggamma_draw(conc[i], uint64_t(seed), uint64_t(idx));
+    }
+}
+
+// x -= logsumexp(x) over groups of A1 (get_var_probs.py:175)
+__global__ void log_normalize_kernel(double* __restrict__ x, int64_t groups, int A1) {
+    for (int64_t g = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; g < groups; g += int64_t(gridDim.x) * blockDim.x) {
+        double* v = x + g * A1;
+        double m = -INFINITY;
+        for (int b = 0; b < A1; ++b) m = fmax(m, v[b]);
+        double s = 0.0;
+        for (int b = 0; b < A1; ++b) s += exp(v[b] - m);
+        const double lse = m + log(s);
+        for (int b = 0; b < A1; ++b) v[b] -= lse;
+    }
+}
+
+}  // namespace
+
+#define ST(stream) static_cast<cudaStream_t>(stream)
+
+extern "C" int bear_decode_onehot(const uint64_t* d_kmers, int64_t n, int lag, int alphabet, double* d_onehot, void* stream) {
+    const char* fn = "bear_decode_onehot";
+    BEAR_REQUIRE(bear_alphabet_size(alphabet) > 0 && lag >= 1 && lag <= bear_max_lag(alphabet) && n >= 0, fn);
+    if (n == 0) return BEAR_OK;
+    BEAR_REQUIRE(d_kmers && d_onehot, fn);
+    decode_onehot_kernel<<<blocks_for(n * lag), THREADS, 0, ST(stream)>>>(d_kmers, n, lag, alphabet, bear_alphabet_size(alphabet) + 1, d_onehot);
+    BEAR_LAUNCH_CHECK("decode_onehot_kernel");
+    return BEAR_OK;
+}
+
+extern "C" int bear_decode_symbols(const uint64_t* d_kmers, int64_t n, int lag, int alphabet, uint8_t* d_sym, void* stream) {
+    const char* fn = "bear_decode_symbols";
+    BEAR_REQUIRE(bear_alphabet_size(alphabet) > 0 && lag >= 1 && lag <= bear_max_lag(alphabet) && n >= 0, fn);
+    if (n == 0) return BEAR_OK;
+    BEAR_REQUIRE(d_kmers && d_sym, fn);
+    decode_symbols_kernel<<<blocks_for(n * lag), THREADS, 0, ST(stream)>>>(d_kmers, n, lag, alphabet, d_sym);
+    BEAR_LAUNCH_CHECK("decode_symbols_kernel");
+    return BEAR_OK;
+}
+
+extern "C" int bear_unpack_counts(const uint32_t* d_counts, int64_t stride, int64_t row0, int64_t n, int G, int A1,
+                                  double* d_out, void* stream) {
+    const char* fn = "bear_unpack_counts";
+    BEAR_REQUIRE(n >= 0 && row0 >= 0 && stride >= row0 + n && G >= 1 && A1 >= 2, fn);
+    if (n == 0) return BEAR_OK;
+    BEAR_REQUIRE(d_counts && d_out, fn);
+    unpack_counts_kernel<<<blocks_for(n * G * A1), THREADS, 0, ST(stream)>>>(d_counts + row0, stride, n, G, A1, d_out);
+    BEAR_LAUNCH_CHECK("unpack_counts_kernel");
+    return BEAR_OK;
+}
+
+#define BEAR_DENSE_ARGS(fn, a, rows, v, n, A1)                                                    \
+    BEAR_REQUIRE(n >= 0 && rows >= 1 && A1 >= 1 && A1 <= MAX_A1 && (n % rows) == 0, fn);          \
+    if (n == 0) return BEAR_OK;                                                                   \
+    BEAR_REQUIRE(a && v, fn)
+
+extern "C" int bear_dm_logprob(const double* d_conc, int64_t conc_rows, const double* d_value, int64_t n, int A1,
+                               double* d_out, void* stream) {
+    BEAR_DENSE_ARGS("bear_dm_logprob", d_conc, conc_rows, d_value, n, A1);
+    BEAR_REQUIRE(d_out != nullptr, "bear_dm_logprob");
+    dm_logprob_kernel<<<blocks_for(n), THREADS, 0, ST(stream)>>>(d_conc, conc_rows, d_value, n, A1, d_out);
+    BEAR_LAUNCH_CHECK("dm_logprob_kernel");
+    return BEAR_OK;
+}
+
+extern "C" int bear_dm_logprob_bwd(const double* d_conc, int64_t conc_rows, const double* d_value, int64_t n, int A1,
+                                   const double* d_gout, double* d_gconc, void* stream) {
+    BEAR_DENSE_ARGS("bear_dm_logprob_bwd", d_conc, conc_rows, d_value, n, A1);
+    BEAR_REQUIRE(d_gconc != nullptr, "bear_dm_logprob_bwd");
+    dm_logprob_bwd_kernel<<<blocks_for(n), THREADS, 0, ST(stream)>>>(d_conc, conc_rows, d_value, n, A1, d_gout, d_gconc);
+    BEAR_LAUNCH_CHECK("dm_logprob_bwd_kernel");
+    return BEAR_OK;
+}
+
+extern "C" int bear_mn_logprob(const double* d_probs, int64_t probs_rows, const double* d_value, int64_t n, int A1,
+                               double* d_out, void* stream) {
+    BEAR_DENSE_ARGS("bear_mn_logprob", d_probs, probs_rows, d_value, n, A1);
+    BEAR_REQUIRE(d_out != nullptr, "bear_mn_logprob");
+    mn_logprob_kernel<<<blocks_for(n), THREADS, 0, ST(stream)>>>(d_probs, probs_rows, d_value, n, A1, d_out);
+    BEAR_LAUNCH_CHECK("mn_logprob_kernel");
+    return BEAR_OK;
+}
+
+extern "C" int bear_mn_logprob_bwd(const double* d_probs, int64_t probs_rows, const double* d_value, int64_t n, int A1,
+                                   const double* d_gout, double* d_gprobs, void* stream) {
+    BEAR_DENSE_ARGS("bear_mn_logprob_bwd", d_probs, probs_rows, d_value, n, A1);
+    BEAR_REQUIRE(d_gprobs != nullptr, "bear_mn_logprob_bwd");
+    mn_logprob_bwd_kernel<<<blocks_for(n), THREADS, 0, ST(stream)>>>(d_probs, probs_rows, d_value, n, A1, d_gout, d_gprobs);
+    BEAR_LAUNCH_CHECK("mn_logprob_bwd_kernel");
+    return BEAR_OK;
+}
+
+extern "C" int bear_ml_output(const double* d_x, int64_t n, int A1, double sigma, int64_t seed, double* d_out, void* stream) {
+    const char* fn = "bear_ml_output";
+    BEAR_REQUIRE(n >= 0 && A1 >= 1, fn);
+    if (n == 0) return BEAR_OK;
+    BEAR_REQUIRE(d_x && d_out, fn);
+    ml_output_kernel<<<blocks_for(n), THREADS, 0, ST(stream)>>>(d_x, n, A1, sigma, seed, d_out);
+    BEAR_LAUNCH_CHECK("ml_output_kernel");
+    return BEAR_OK;
+}
+
+extern "C" int bear_loggamma_sample(const double* d_conc, int64_t n, int64_t n_samples, int64_t seed, double* d_out, void* stream) {
+    const char* fn = "bear_loggamma_sample";
+    BEAR_REQUIRE(n >= 0 && n_samples >= 0, fn);
+    if (n == 0 || n_samples == 0) return BEAR_OK;
+    BEAR_REQUIRE(d_conc && d_out, fn);
+    loggamma_sample_kernel<<<blocks_for(n * n_samples), THREADS, 0, ST(stream)>>>(d_conc, n, n_samples, seed, d_out);
+    BEAR_LAUNCH_CHECK("loggamma_sample_kernel");
+    return BEAR_OK;
+}
+
+extern "C" int bear_log_normalize(double* d_x, int64_t n_groups, int A1, void* stream) {
+    const char* fn = "bear_log_normalize";
+    BEAR_REQUIRE(n_groups >= 0 && A1 >= 1, fn);
+    if (n_groups == 0) return BEAR_OK;
+    BEAR_REQUIRE(d_x != nullptr, fn);
+    log_normalize_kernel<<<blocks_for(n_groups), THREADS, 0, ST(stream)>>>(d_x, n_groups, A1);
+    BEAR_LAUNCH_CHECK("log_normalize_kernel");
+    return BEAR_OK;
+}

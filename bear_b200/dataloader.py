@@ -1,0 +1,319 @@
+"""Packed, device-resident k-mer count tables and the BMM marginal likelihood.
+
+Mirrors the reference's ``bear_model/dataloader.py`` API (``dataloader``, ``sparse_dataloader``,
+``bmm_likelihood``), but instead of a ``tf.data`` pipeline of byte strings and float64 count tensors
+(dataloader.py:36-46, 82-105) the text is parsed ONCE by the C++ packer into
+``uint64`` 2-bit packed k-mers + group-planar ``uint32`` counts, uploaded, and kept resident in HBM.
+The fused kernels stream that table directly; iterating a dataset still yields the reference's
+``(kmers, counts[B, G, A+1])`` batches (unpacked on the device) for API compatibility.
+"""
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import lib, check, ptr
+
+ALPHABET_SIZES = {'dna': 4, 'rna': 4, 'prot': 20}
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class KmerBatch:
+    """The k-mer half of a batch: packed codes on the device; ``.numpy()`` gives the byte strings the
+    reference's ``kmers.numpy()`` would (dataloader.py:46)."""
+
+    def __init__(self, packed, lag, alphabet):
+        self.packed, self.lag, self.alphabet = packed, lag, alphabet
+
+    def __len__(self):
+        return int(self.packed.shape[0])
+
+    def numpy(self):
+        return decode_kmers(self.packed.cpu().numpy().view(np.uint64), self.lag, self.alphabet)
+
+
+def encode_kmers(kmers, alphabet):
+    """list / array of equal-length k-mer strings (or bytes) -> uint64 packed codes (numpy), lag."""
+    kmers = [k.decode() if isinstance(k, (bytes, np.bytes_)) else str(k) for k in np.asarray(kmers).ravel()]
+    n = len(kmers)
+    lag = len(kmers[0]) if n else 1
+    if any(len(k) != lag for k in kmers):
+        raise ValueError('k-mers must all have the same length')
+    out = np.empty(n, dtype=np.uint64)
+    text = ''.join(kmers).encode()
+    check(lib.bear_encode_kmers(text, n, lag, _lib.ALPHABET_IDS[alphabet], ptr(out)))
+    return out, lag
+
+
+def decode_kmers(packed, lag, alphabet):
+    packed = np.ascontiguousarray(packed, dtype=np.uint64)
+    buf = np.empty(packed.size * lag, dtype=np.uint8)
+    check(lib.bear_decode_kmers(ptr(packed), packed.size, lag, _lib.ALPHABET_IDS[alphabet], ptr(buf)))
+    return buf.view('S%d' % lag) if packed.size else np.empty(0, dtype='S%d' % lag)
+
+
+class KmerTable:
+    """A packed table: ``kmers`` uint64 [K] and ``counts`` uint32 [G, A1, stride] (host numpy arrays,
+    uploaded lazily).  ``stride`` is the plane pitch (multiple of 4 elements)."""
+
+    def __init__(self, kmers, counts, num_rows, lag, alphabet):
+        self.kmers_host = kmers
+        self.counts_host = counts
+        self.num_rows = int(num_rows)
+        self.lag = int(lag)
+        self.alphabet = alphabet
+        self.num_ds = int(counts.shape[0])
+        self.A1 = int(counts.shape[1])
+        self.stride = int(counts.shape[2])
+        self._dev = None
+
+    # -- construction -------------------------------------------------------------------------
+    @classmethod
+    def from_file(cls, file, alphabet, num_ds, sparse=False, header=None):
+        if header is None:
+            header = bool(sparse)
+        path = os.fsencode(file)
+        K = lib.bear_count_rows(path, int(header))
+        check(K)
+        A1 = ALPHABET_SIZES[alphabet] + 1
+        stride = max(_round_up(K, 4), 4)
+        kmers = np.zeros(stride, dtype=np.uint64)
+        counts = np.zeros((num_ds, A1, stride), dtype=np.uint32)
+        rows, lag = ctypes.c_int64(0), ctypes.c_int(0)
+        fn = lib.bear_pack_sparse if sparse else lib.bear_pack_tsv
+        check(fn(path, int(header), _lib.ALPHABET_IDS[alphabet], num_ds, 0, K, ptr(kmers), ptr(counts), stride,
+                 ctypes.byref(rows), ctypes.byref(lag)))
+        return cls(kmers, counts, rows.value, max(lag.value, 1), alphabet)
+
+    @classmethod
+    def from_arrays(cls, kmers, counts, alphabet):
+        """kmers: strings or uint64 codes with ``lag`` given as (codes, lag); counts [K, G, A1] integers."""
+        if isinstance(kmers, tuple):
+            codes, lag = kmers
+            codes = np.ascontiguousarray(codes, dtype=np.uint64)
+        else:
+            codes, lag = encode_kmers(kmers, alphabet)
+        counts = np.asarray(counts)
+        K, G, A1 = counts.shape
+        if A1 != ALPHABET_SIZES[alphabet] + 1:
+            raise ValueError('counts last axis must be alphabet_size + 1')
+        if np.any(counts < 0) or np.any(counts != np.floor(counts)) or np.any(counts > 4294967295):
+            raise ValueError('counts must be integers in [0, 2^32)')
+        stride = max(_round_up(K, 4), 4)
+        k = np.zeros(stride, dtype=np.uint64)
+        k[:K] = codes
+        c = np.zeros((G, A1, stride), dtype=np.uint32)
+        c[:, :, :K] = np.transpose(counts.astype(np.uint32), (1, 2, 0))
+        return cls(k, c, K, lag, alphabet)
+
+    @classmethod
+    def from_device(cls, kmers_dev, counts_dev, num_rows, lag, alphabet):
+        """Adopt device tensors (int64 [stride], int32 [G, A1, stride]) produced on the GPU
+        (synthetic benchmark tables); no host copy exists."""
+        self = cls.__new__(cls)
+        self.kmers_host = self.counts_host = None
+        self.num_rows, self.lag, self.alphabet = int(num_rows), int(lag), alphabet
+        self.num_ds, self.A1, self.stride = (int(s) for s in counts_dev.shape)
+        self._dev = (kmers_dev, counts_dev)
+        return self
+
+    @classmethod
+    def concat(cls, tables):
+        t0 = tables[0]
+        K = sum(t.num_rows for t in tables)
+        stride = max(_round_up(K, 4), 4)
+        kmers = np.zeros(stride, dtype=np.uint64)
+        counts = np.zeros((t0.num_ds, t0.A1, stride), dtype=np.uint32)
+        o = 0
+        for t in tables:
+            if (t.lag, t.alphabet, t.num_ds) != (t0.lag, t0.alphabet, t0.num_ds):
+                raise ValueError('tables differ in lag / alphabet / num_ds')
+            kmers[o:o + t.num_rows] = t.kmers_host[:t.num_rows]
+            counts[:, :, o:o + t.num_rows] = t.counts_host[:, :, :t.num_rows]
+            o += t.num_rows
+        return cls(kmers, counts, K, t0.lag, t0.alphabet)
+
+    def take(self, index):
+        """Rows ``index`` (numpy int array) as a new host table."""
+        index = np.asarray(index, dtype=np.int64)
+        K = index.size
+        stride = max(_round_up(K, 4), 4)
+        kmers = np.zeros(stride, dtype=np.uint64)
+        counts = np.zeros((self.num_ds, self.A1, stride), dtype=np.uint32)
+        kmers[:K] = self.kmers_host[index]
+        counts[:, :, :K] = self.counts_host[:, :, index]
+        return KmerTable(kmers, counts, K, self.lag, self.alphabet)
+
+    # -- device residency ---------------------------------------------------------------------
+    def device_tensors(self):
+        """(kmers int64 [stride], counts int32 [G, A1, stride]) on the current CUDA device; the bit
+        patterns are the uint64 / uint32 of the packed layout."""
+        if self._dev is None:
+            dev = _lib.device()
+            k = torch.from_numpy(self.kmers_host.view(np.int64)).pin_memory().to(dev, non_blocking=True)
+            c = torch.from_numpy(self.counts_host.view(np.int32)).pin_memory().to(dev, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            self._dev = (k, c)
+        return self._dev
+
+    def col_ptr(self, ds_loc):
+        """Device address of plane 0 of count column ``ds_loc``."""
+        _, c = self.device_tensors()
+        if not 0 <= ds_loc < self.num_ds:
+            raise IndexError('count column %d out of range (num_ds=%d)' % (ds_loc, self.num_ds))
+        return ctypes.c_void_p(c.data_ptr() + 4 * ds_loc * self.A1 * self.stride)
+
+    def kmers_str(self, row0=0, n=None):
+        n = self.num_rows - row0 if n is None else n
+        if self.kmers_host is None:
+            host = self._dev[0][row0:row0 + n].cpu().numpy().view(np.uint64)
+        else:
+            host = self.kmers_host[row0:row0 + n]
+        return decode_kmers(host, self.lag, self.alphabet)
+
+
+class KmerDataset:
+    """What ``dataloader`` returns: a packed table cut into minibatches of ``batch_size`` consecutive
+    rows (dataloader.py:37), optionally repeated (``.repeat(epochs)``, models/train_bear_net.py:87).
+
+    Under ``torch.distributed`` each rank keeps only its contiguous slice of every global batch
+    (``shard(rank, world)``); the fused kernels see the local slices, ``global_batch_rows`` keeps the
+    reference's ``num_kmers / batch`` factor (bear_net.py:190) independent of the GPU count.
+    """
+
+    def __init__(self, table, batch_size, repeats=1, ranges=None, global_rows=None, map_fn=None):
+        self.table = table
+        self.batch_size = int(batch_size)
+        self.repeats = int(repeats)
+        K = table.num_rows
+        if ranges is None:
+            ranges = [(r0, min(self.batch_size, K - r0)) for r0 in range(0, K, self.batch_size)]
+            global_rows = [n for _, n in ranges]
+        self.ranges = ranges                  # local (row0, n) per batch
+        self.global_rows = global_rows        # rows of the same batch summed over all ranks
+        self.map_fn = map_fn
+
+    # tf.data-like surface used by the reference scripts
+    def repeat(self, count):
+        return KmerDataset(self.table, self.batch_size, self.repeats * int(count), self.ranges, self.global_rows, self.map_fn)
+
+    def cache(self):
+        return self
+
+    def prefetch(self, n):
+        return self
+
+    def map(self, fn, num_parallel_calls=None):
+        prev = self.map_fn
+        f = fn if prev is None else (lambda *a: fn(*_as_tuple(prev(*a))))
+        return KmerDataset(self.table, self.batch_size, self.repeats, self.ranges, self.global_rows, f)
+
+    def __len__(self):
+        return len(self.ranges) * self.repeats
+
+    def batches(self):
+        """(row0, n_local, n_global) for every step, repeats included."""
+        for _ in range(self.repeats):
+            for (r0, n), g in zip(self.ranges, self.global_rows):
+                yield r0, n, g
+
+    def shard(self, rank, world):
+        """This rank's contiguous slice of every batch, gathered into a table of its own."""
+        if world == 1:
+            return self
+        if self.table.kmers_host is None:
+            raise ValueError('shard() needs a host table; device-generated tables are built per rank')
+        idx, ranges, grows, o = [], [], [], 0
+        for r0, n in self.ranges:
+            per = -(-n // world)
+            lo, hi = min(rank * per, n), min((rank + 1) * per, n)
+            idx.append(np.arange(r0 + lo, r0 + hi))
+            ranges.append((o, hi - lo))
+            grows.append(n)
+            o += hi - lo
+        local = self.table.take(np.concatenate(idx) if idx else np.zeros(0, np.int64))
+        return KmerDataset(local, self.batch_size, self.repeats, ranges, grows, self.map_fn)
+
+    def __iter__(self):
+        """Yields the reference's batch elements: (KmerBatch, counts float64 [B, G, A1] on the device),
+        passed through ``map`` functions if any."""
+        t = self.table
+        k, c = t.device_tensors()
+        for r0, n, _ in self.batches():
+            out = torch.empty((n, t.num_ds, t.A1), dtype=torch.float64, device=k.device)
+            check(lib.bear_unpack_counts(ptr(c), t.stride, r0, n, t.num_ds, t.A1, ptr(out), _lib.stream()))
+            item = (KmerBatch(k[r0:r0 + n], t.lag, t.alphabet), out)
+            yield item if self.map_fn is None else self.map_fn(*item)
+
+
+def _as_tuple(x):
+    return x if isinstance(x, tuple) else (x,)
+
+
+def _local_shard(ds):
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return ds.shard(dist.get_rank(), dist.get_world_size())
+    return ds
+
+
+def dataloader(file, alphabet, batch_size, num_ds, cache=True, header=False, n_par=1, dtype=torch.float64):
+    """Dense TSV ``kmer \\t [[counts g0],[counts g1],...]`` -> KmerDataset (reference:
+    dataloader.py:6-50).  ``cache`` / ``n_par`` are accepted for signature parity; the packed table is
+    always resident."""
+    table = KmerTable.from_file(file, alphabet, num_ds, sparse=False, header=header)
+    return _local_shard(KmerDataset(table, batch_size))
+
+
+def sparse_dataloader(file, alphabet, batch_size, num_ds, cache=False, header=True, n_par=1, dtype=torch.float64):
+    """Sparse ``kmer; [[g,b],...]; [v,...]`` file -> KmerDataset (reference: dataloader.py:52-109)."""
+    table = KmerTable.from_file(file, alphabet, num_ds, sparse=True, header=header)
+    return _local_shard(KmerDataset(table, batch_size))
+
+
+def load_files(files, alphabet, batch_size, num_ds, sparse=False, header=None):
+    """Several files of one dataset (models/train_bear_net.py:78-86 interleaves them; here they are
+    concatenated in name order into one resident table)."""
+    tables = [KmerTable.from_file(f, alphabet, num_ds, sparse=sparse, header=header) for f in sorted(files)]
+    table = tables[0] if len(tables) == 1 else KmerTable.concat(tables)
+    return _local_shard(KmerDataset(table, batch_size))
+
+
+def count_rows(file, header=False):
+    """`wc -l` of models/train_bear_net.py:54-55 (non-empty data rows)."""
+    return check(lib.bear_count_rows(os.fsencode(file), int(header)))
+
+
+def _allreduce_sum(t):
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
+def bmm_likelihood(data, alpha, dtype=torch.float64):
+    """BMM marginal log-likelihood of every count column for every prior in ``alpha`` -> [num_ds, V]
+    (reference: dataloader.py:111-147).  ``data`` is a KmerDataset (a ``.map(lambda k, c: c)`` view of
+    it is accepted, as in the reference's usage); the packed table is streamed once by
+    ``bear_bmm_likelihood``, and the [G, V] partial sums are allreduced once at the end."""
+    if not isinstance(data, KmerDataset):
+        raise TypeError('bmm_likelihood needs a KmerDataset (from dataloader / sparse_dataloader)')
+    t = data.table
+    k, c = t.device_tensors()
+    alpha = torch.as_tensor(np.asarray(alpha, dtype=np.float64)).reshape(-1)
+    V = alpha.numel()
+    out = torch.zeros((t.num_ds, V), dtype=torch.float64, device=k.device)
+    ws = torch.empty(lib.bear_workspace_doubles(t.num_rows, t.lag, 0), dtype=torch.float64, device=k.device)
+    for v0 in range(0, V, _lib.MAX_MODELS):
+        a = alpha[v0:v0 + _lib.MAX_MODELS].to(k.device)
+        part = torch.zeros((t.num_ds, a.numel()), dtype=torch.float64, device=k.device)
+        for r0, n, _ in data.batches():
+            check(lib.bear_bmm_likelihood(ptr(c), t.stride, r0, n, t.num_ds, t.A1, ptr(a), a.numel(), ptr(part),
+                                          ptr(ws), _lib.stream()))
+        out[:, v0:v0 + a.numel()] = part
+    return _allreduce_sum(out).cpu()
