@@ -198,6 +198,72 @@ __global__ void log_normalize_kernel(double* __restrict__ x, int64_t groups, int
     }
 }
 
+
+// Deterministic synthetic table (bench / large-scale parity): every cell is a pure function of
+// (seed, global row index), so any shard of any size regenerates the same rows.
+//   k-mer : code = (row * ODD + OFFSET) mod 4^lag -- a bijection of the row index, pseudo-random
+//           order (the reference recommends shuffled tables, docs/usage.rst:191-194); a
+//           start_permille/1000 slice gets a start-padded prefix.
+//   counts: regime 0 "sparse": N = 1 + Poisson(2) transitions, each to the row's dominant letter
+//           with probability 0.7 else uniform over the 4 letters, the last one a stop w.p. 1/150;
+//           regime 1 "dense": N = round(LogNormal(ln 300, 1.5)) split by a row-specific profile.
+//           Columns g > 0 are binomial thinnings (1/4) of column 0, as ysd1's train:test ratio.
+__global__ void synth_table_kernel(uint64_t* __restrict__ kmers, uint32_t* __restrict__ counts, int64_t stride,
+                                   int64_t row_begin, int64_t n, int lag, int G, int64_t seed, int regime,
+                                   int start_permille) {
+    const uint64_t mask = lag >= 29 ? ((1ull << 58) - 1) : ((1ull << (2 * lag)) - 1);
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+        const uint64_t row = uint64_t(row_begin + i);
+        uint64_t code = (row * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull * uint64_t(seed + 1)) & mask;
+        const uint64_t hs = rng_u64(uint64_t(seed), row, 1);
+        if (int(hs % 1000) < start_permille) {
+            const uint64_t ns = 1 + (hs >> 20) % uint64_t(lag);
+            code &= ns >= uint64_t(lag) ? 0ull : ((1ull << (2 * (lag - int(ns)))) - 1);
+            code |= ns << 58;
+        }
+        kmers[i] = code;
+        uint32_t c[5] = {0, 0, 0, 0, 0};
+        const uint64_t h0 = rng_u64(uint64_t(seed), row, 2);
+        const int dom = int(h0 & 3);
+        if (regime == 0) {
+            double u = u01(rng_u64(uint64_t(seed), row, 3));
+            int N = 1;
+            double p = 0.1353352832366127, cdf = p;     // Poisson(2)
+            while (u > cdf && N < 40) { p *= 2.0 / double(N); cdf += p; ++N; }
+            for (int t = 0; t < N; ++t) {
+                const uint64_t ht = rng_u64(uint64_t(seed), row, 16 + uint64_t(t));
+                const int letter = (ht % 10) < 7 ? dom : int((ht >> 8) & 3);
+                if (t == N - 1 && (ht >> 16) % 150 == 0) c[4]++;
+                else c[letter]++;
+            }
+        } else {
+            const double z = rng_normal(uint64_t(seed), row, 3);
+            const double N = rint(exp(5.703782474656201 + 1.5 * z));
+            double w[5], ws = 0.0;
+            for (int b = 0; b < 5; ++b) {
+                w[b] = -log(u01(rng_u64(uint64_t(seed), row, 8 + uint64_t(b)))) * (b == dom ? 3.0 : (b == 4 ? 0.03 : 1.0));
+                ws += w[b];
+            }
+            for (int b = 0; b < 5; ++b) c[b] = uint32_t(fmin(rint(N * w[b] / ws), 4.0e9));
+        }
+        for (int b = 0; b < 5; ++b) counts[int64_t(b) * stride + i] = c[b];
+        for (int g = 1; g < G; ++g) {
+            for (int b = 0; b < 5; ++b) {
+                uint32_t t = 0;
+                if (c[b] <= 64) {
+                    for (uint32_t k = 0; k < c[b]; ++k)
+                        t += (rng_u64(uint64_t(seed), row, 1000 * uint64_t(g) + 64 * uint64_t(b) + k) & 3) == 0;
+                } else {
+                    const double m = 0.25 * double(c[b]), sd = sqrt(0.1875 * double(c[b]));
+                    const double x = rint(m + sd * rng_normal(uint64_t(seed), row, 1000 * uint64_t(g) + uint64_t(b)));
+                    t = uint32_t(fmin(fmax(x, 0.0), double(c[b])));
+                }
+                counts[(int64_t(g) * 5 + b) * stride + i] = t;
+            }
+        }
+    }
+}
+
 }  // namespace
 
 #define ST(stream) static_cast<cudaStream_t>(stream)
@@ -301,5 +367,18 @@ extern "C" int bear_log_normalize(double* d_x, int64_t n_groups, int A1, void* s
     BEAR_REQUIRE(d_x != nullptr, fn);
     log_normalize_kernel<<<blocks_for(n_groups), THREADS, 0, ST(stream)>>>(d_x, n_groups, A1);
     BEAR_LAUNCH_CHECK("log_normalize_kernel");
+    return BEAR_OK;
+}
+
+extern "C" int bear_synth_table(uint64_t* d_kmers, uint32_t* d_counts, int64_t stride, int64_t row_begin, int64_t n,
+                                int lag, int G, int64_t seed, int regime, int start_permille, void* stream) {
+    const char* fn = "bear_synth_table";
+    BEAR_REQUIRE(n >= 0 && stride >= n && lag >= 1 && lag <= 29 && G >= 1 && row_begin >= 0, fn);
+    BEAR_REQUIRE(regime == 0 || regime == 1, fn);
+    if (n == 0) return BEAR_OK;
+    BEAR_REQUIRE(d_kmers && d_counts, fn);
+    synth_table_kernel<<<blocks_for(n), THREADS, 0, ST(stream)>>>(d_kmers, d_counts, stride, row_begin, n, lag, G, seed,
+                                                                  regime, start_permille);
+    BEAR_LAUNCH_CHECK("synth_table_kernel");
     return BEAR_OK;
 }

@@ -152,9 +152,9 @@ def test_lgamma_difference_accuracy(cuda):
         a, b, c = mp.mpf(cc[0]), mp.mpf(cc[1]), mp.mpf(vv[0])
         want = (mp.loggamma(a + c) - mp.loggamma(a)) - (mp.loggamma(a + b + c) - mp.loggamma(a + b))
         dwant = (mp.digamma(a + c) - mp.digamma(a)) - (mp.digamma(a + b + c) - mp.digamma(a + b))
-        scale = max(abs(mp.loggamma(a + c) - mp.loggamma(a)), mp.mpf(1e-300))
+        scale = max(abs(mp.loggamma(a + c) - mp.loggamma(a)), abs(mp.loggamma(a + b + c) - mp.loggamma(a + b)), mp.mpf(1e-300))
         assert abs(got[i] - want) <= 2e-14 * scale + 1e-300, (cc, vv, got[i], want)
-        dscale = max(abs(mp.digamma(a + c) - mp.digamma(a)), mp.mpf(1e-300))
+        dscale = max(abs(mp.digamma(a + c) - mp.digamma(a)), abs(mp.digamma(a + b + c) - mp.digamma(a + b)), mp.mpf(1e-300))
         assert abs(grad[i, 0] - dwant) <= 2e-14 * dscale + 1e-300, (cc, vv, grad[i, 0], dwant)
 
 
