@@ -113,7 +113,7 @@ def read_sparse(path, num_ds, alphabet='dna', header=True):
 # distributions (core.py)
 # ----------------------------------------------------------------------------
 def _t(x, dtype=torch.float64):
-    return x if isinstance(x, torch.Tensor) else torch.as_tensor(np.asarray(x), dtype=dtype)
+    return x if isinstance(x, torch.Tensor) else torch.as_tensor(np.array(x, dtype=np.float64), dtype=dtype)
 
 
 def lbeta(x):

@@ -1,0 +1,164 @@
+"""CPU tests of the boundary: the C-ABI library loads and exports every symbol include/bear_b200.h
+declares (no compute calls without a GPU), and the host packer reproduces the reference's text
+formats bit-exactly (dataloader.py:6-109, core.py:142-174)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, SPARSE, YSD1
+from oracle import bear_oracle as O
+
+
+def test_library_exports_every_declared_symbol():
+    from bear_b200 import _lib
+    header = open(os.path.join(ROOT, 'include', 'bear_b200.h')).read()
+    header = re.sub(r'/\*.*?\*/', '', header, flags=re.S)
+    declared = sorted(set(re.findall(r'\b(bear_[a-z0-9_]+)\s*\(', header)))
+    assert len(declared) >= 28
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(raw, name), 'symbol %s declared in bear_b200.h is not exported' % name
+    assert set(_lib.EXPORTS) == set(declared), 'ctypes signatures and header disagree'
+    assert _lib.lib.bear_version() == 1
+    assert [_lib.lib.bear_alphabet_size(a) for a in (0, 1, 2, 3)] == [4, 4, 20, -1]
+    assert [_lib.lib.bear_max_lag(a) for a in (0, 1, 2)] == [29, 29, 12]
+
+
+def test_missing_library_fails_loudly(tmp_path, monkeypatch):
+    """No fallback: a missing .so is an ImportError with a build hint."""
+    import importlib
+    from bear_b200 import _lib
+    monkeypatch.setattr(_lib, 'LIB_PATH', str(tmp_path / 'nope.so'))
+    with pytest.raises(ImportError, match='no CPU or pure-PyTorch fallback'):
+        _lib._load()
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, 'bear_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.cpp', '.h')):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle', src, flags=re.M), f
+
+
+def test_compute_entry_points_need_cuda():
+    import torch
+    from bear_b200 import _lib
+    if torch.cuda.is_available():
+        pytest.skip('CPU-only check')
+    with pytest.raises(_lib.BearError, match='no CPU fallback'):
+        _lib.device()
+
+
+# ------------------------------------------------------------------------------------------------
+def test_pack_tsv_matches_oracle_reader_bit_exact():
+    from bear_b200 import dataloader as dl
+    t = dl.KmerTable.from_file(YSD1, 'dna', 3)
+    kmers, counts = O.read_tsv(YSD1, 3)
+    assert t.num_rows == 1365 == dl.count_rows(YSD1) and t.lag == 5 and t.stride % 4 == 0
+    assert [k.decode() for k in t.kmers_str()] == kmers
+    got = np.transpose(t.counts_host[:, :, :t.num_rows], (2, 0, 1))
+    assert np.array_equal(got.astype(np.float64), counts)
+    assert not t.counts_host[:, :, t.num_rows:].any()          # padding rows are zero
+
+
+def test_pack_sparse_matches_oracle_reader():
+    from bear_b200 import dataloader as dl
+    t = dl.KmerTable.from_file(SPARSE, 'dna', 1, sparse=True)
+    kmers, counts = O.read_sparse(SPARSE, 1)
+    assert [k.decode() for k in t.kmers_str()] == kmers
+    assert np.array_equal(np.transpose(t.counts_host[:, :, :t.num_rows], (2, 0, 1)).astype(float), counts)
+    # the dense TSV twins of the same toy sequences agree row for row
+    twin = dl.KmerTable.from_file(os.path.join(os.path.dirname(SPARSE), 'kmaps', 'ex_seqs_lag_3_file_0.tsv'), 'dna', 1)
+    a = dict(zip(t.kmers_str().tolist(), t.counts_host[0, :, :t.num_rows].T.tolist()))
+    b = dict(zip(twin.kmers_str().tolist(), twin.counts_host[0, :, :twin.num_rows].T.tolist()))
+    assert a == b
+
+
+@pytest.mark.parametrize('alphabet,lag', [('dna', 1), ('dna', 13), ('dna', 20), ('dna', 29), ('rna', 7), ('prot', 12), ('prot', 3)])
+def test_encode_decode_round_trip(alphabet, lag):
+    from bear_b200 import dataloader as dl
+    rng = np.random.default_rng(lag)
+    letters = O.ALPHABETS_IN[alphabet][:-1]
+    kmers = []
+    for _ in range(500):
+        ns = int(rng.integers(0, lag + 1)) if rng.random() < 0.3 else 0
+        kmers.append('[' * ns + ''.join(rng.choice(letters, size=lag - ns)))
+    codes, got_lag = dl.encode_kmers(kmers, alphabet)
+    assert got_lag == lag
+    assert [k.decode() for k in dl.decode_kmers(codes, lag, alphabet)] == kmers
+    if alphabet != 'prot':
+        # numeric order of the payload = lexicographic order of start-free k-mers
+        plain = sorted(k for k in kmers if '[' not in k)
+        order = {'A': 0, 'C': 1, 'G': 2, 'T': 3, 'U': 3}
+        pc, _ = dl.encode_kmers(plain, alphabet) if plain else (np.zeros(0, np.uint64), lag)
+        assert np.all(np.diff(pc.astype(np.int64)) >= 0)
+        for k, c in zip(plain[:20], pc[:20]):
+            assert int(c) == sum(order[ch] << (2 * (lag - 1 - j)) for j, ch in enumerate(k))
+
+
+def _write(tmp_path, text, name='t.tsv'):
+    p = tmp_path / name
+    p.write_text(text)
+    return str(p)
+
+
+def test_pack_error_cases(tmp_path):
+    from bear_b200 import dataloader as dl
+    from bear_b200._lib import BearError
+    ok = 'ACG\t[[1,2,3,4,5]]\n'
+    cases = {
+        'outside the alphabet': 'ANG\t[[1,2,3,4,5]]\n',
+        "start symbol '\\[' after a letter": 'A[G\t[[1,2,3,4,5]]\n',
+        'length 2 differs from 3': ok + 'AC\t[[1,2,3,4,5]]\n',
+        'negative or not an integer': 'ACG\t[[1,2.5,3,4,5]]\n',
+        'exceeds uint32': 'ACG\t[[1,2,3,4,5000000000]]\n',
+        'no tab separator': 'ACG [[1,2,3,4,5]]\n',
+        "expected ','": 'ACG\t[[1,2,3,4]]\n',
+        'wrong alphabet size': 'ACG\t[[1,2,3,4,5,6]]\n',
+        'wrong num_ds': 'ACG\t[[1,2,3,4,5],[1,2,3,4,5]]\n',
+    }
+    for msg, text in cases.items():
+        with pytest.raises(BearError, match=msg):
+            dl.KmerTable.from_file(_write(tmp_path, text), 'dna', 1)
+    with pytest.raises(BearError, match='cannot open'):
+        dl.KmerTable.from_file(str(tmp_path / 'absent.tsv'), 'dna', 1)
+    with pytest.raises(BearError, match='exceeds the packed layout'):
+        dl.KmerTable.from_file(_write(tmp_path, 'A' * 30 + '\t[[1,2,3,4,5]]\n'), 'dna', 1)
+
+
+def test_pack_edge_inputs(tmp_path):
+    from bear_b200 import dataloader as dl
+    empty = dl.KmerTable.from_file(_write(tmp_path, ''), 'dna', 2)
+    assert empty.num_rows == 0 and len(dl.KmerDataset(empty, 10)) == 0
+    # header line, blank lines, CRLF, float-formatted integers, maximum count
+    text = 'kmer\tcounts\n\nACGT\t[[1.0, 2, 3e0, 4294967295, 0],[0,0,0,0,0]]\r\n[[[A\t[[0,0,0,0,0],[7,0,0,0,1]]\n'
+    t = dl.KmerTable.from_file(_write(tmp_path, text), 'dna', 2, header=True)
+    assert t.num_rows == 2 and t.lag == 4
+    assert t.counts_host[0, :, 0].tolist() == [1, 2, 3, 4294967295, 0]
+    assert t.counts_host[1, :, 1].tolist() == [7, 0, 0, 0, 1]
+    assert [k.decode() for k in t.kmers_str()] == ['ACGT', '[[[A']
+    assert int(t.kmers_host[1] >> np.uint64(58)) == 3
+    ds = dl.KmerDataset(t, 1).repeat(3)
+    assert len(ds) == 6 and [b[:2] for b in ds.batches()] == [(0, 1), (1, 1)] * 3
+
+
+def test_dataset_batching_and_sharding_cover_every_row_once():
+    from bear_b200 import dataloader as dl
+    t = dl.KmerTable.from_file(YSD1, 'dna', 3)
+    ds = dl.KmerDataset(t, 300)
+    assert [n for _, n, _ in ds.batches()] == [300, 300, 300, 300, 165]
+    for world in (2, 3, 8):
+        seen = []
+        for rank in range(world):
+            sh = ds.shard(rank, world)
+            assert [g for _, _, g in sh.batches()] == [300, 300, 300, 300, 165]
+            seen.append(sh.table.kmers_str().tolist())
+            # per batch the local slices of all ranks add up to the global batch
+        assert sorted(sum(seen, [])) == sorted(t.kmers_str().tolist())
+        per_batch = np.sum([[n for _, n, _ in ds.shard(r, world).batches()] for r in range(world)], 0)
+        assert per_batch.tolist() == [300, 300, 300, 300, 165]
