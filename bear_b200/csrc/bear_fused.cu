@@ -4,9 +4,18 @@
 //   explicit_train_kernel the same loss for a caller-evaluated head f (CNN / bear_ref / plugins)
 //   eval_kernel           bear_net._evaluation_step (bear_net.py:323-371), h_scan (bear_net.py:516-531)
 //   bmm_kernel            dataloader._marginal_step (dataloader.py:111-113)
-// Every kernel streams the packed table once (8 B k-mer + 20 B per count column per row), keeps all
-// per-row temporaries in registers and reduces in two deterministic stages: per-CTA partials in the
-// caller's workspace, then a fixed-order sum.
+// Every kernel streams the packed table once (8 B k-mer + 20 B per count column per row) and keeps all
+// per-row temporaries in registers.  What makes the sparse-count regime cheap:
+//   * the linear head is a gather from per-chunk tables of exp-ratios (4 positions per lookup);
+//   * lgamma / digamma differences at small integer offsets are rising factorials evaluated with
+//     predicated straight-line code; terms that do not depend on the row's k-mer (the "total" term of
+//     the Dirichlet-multinomial, BMM priors) come from per-CTA tables indexed by the count;
+//   * log() is taken of running products spanning many rows, not once per row; the five reciprocals
+//     of a row share one division;
+//   * the weight-table gradient is scattered without atomics: rows are staged in shared memory and
+//     each chunk table is owned by one warp, which resolves intra-tile collisions with match.any.
+// Reductions are two-stage and deterministic across CTAs: per-CTA partials in the caller's workspace,
+// then a fixed-order sum.
 #include <math.h>
 
 #include "bear_b200.h"
@@ -21,30 +30,87 @@ constexpr int A1 = 5;            // DNA/RNA letters + stop
 constexpr int CHUNK = 4;         // positions per chunk table
 constexpr int COMBOS = 256;      // 4^CHUNK
 constexpr int THREADS = 256;
+constexpr int NW = THREADS / 32;
 constexpr int MAX_GRID = 148 * 4;
+constexpr int TABN = 64;         // counts below TABN index the per-CTA tables of row-independent terms
+constexpr uint64_t PAYLOAD_MASK = (1ull << 58) - 1;
+constexpr uint64_t KEY_INVALID = ~0ull;
 
 __host__ __device__ inline int num_chunks(int lag) { return (lag + CHUNK - 1) / CHUNK; }
 
 // ------------------------------------------------------------------------------------------------
-// shared pieces
+// per-row pieces
 // ------------------------------------------------------------------------------------------------
-struct Row {
-    double c[A1];
+constexpr uint32_t SMALLC = 8;   // counts up to SMALLC take the predicated rising-factorial path
+
+struct Counts {
+    uint32_t c[A1];
+    uint32_t cmax;
     double n;
 };
 
-__device__ __forceinline__ Row load_row(const uint32_t* __restrict__ col, int64_t stride, int64_t i) {
-    Row r;
-    uint32_t raw[A1];
+__device__ __forceinline__ Counts load_counts(const uint32_t* __restrict__ col, int64_t stride, int64_t i, bool in_range) {
+    Counts r;
 #pragma unroll
-    for (int b = 0; b < A1; ++b) raw[b] = __ldg(col + b * stride + i);
-    r.n = 0.0;
+    for (int b = 0; b < A1; ++b) r.c[b] = in_range ? __ldg(col + b * stride + i) : 0u;
+    r.cmax = max(max(max(r.c[0], r.c[1]), max(r.c[2], r.c[3])), r.c[4]);
+    r.n = (double(r.c[0]) + double(r.c[1])) + (double(r.c[2]) + double(r.c[3])) + double(r.c[4]);
+    return r;
+}
+
+// Warp-uniform trip count of the small-count loops: the largest count (capped) among the live lanes.
+__device__ __forceinline__ uint32_t warp_steps(bool live, uint32_t cmax) {
+    return __reduce_max_sync(0xffffffffu, live ? (cmax < SMALLC ? cmax : SMALLC) : 0u);
+}
+
+// Rising factorials P_b = prod_{i<c_b}(a_b + i) and derivatives D_b for the five letters of a row.
+// `steps` is warp-uniform, the body predicated: no divergence.  Valid for c_b <= SMALLC.
+template <bool GRAD>
+__device__ __forceinline__ void rf_letters(const double (&a)[A1], const uint32_t (&c)[A1], uint32_t steps,
+                                           double (&P)[A1], double (&D)[A1]) {
 #pragma unroll
     for (int b = 0; b < A1; ++b) {
-        r.c[b] = double(raw[b]);
-        r.n += r.c[b];
+        P[b] = c[b] >= 1 ? a[b] : 1.0;
+        D[b] = c[b] >= 1 ? 1.0 : 0.0;
     }
-    return r;
+    for (uint32_t t = 1; t < steps; ++t) {
+        const double td = double(t);
+#pragma unroll
+        for (int b = 0; b < A1; ++b) {
+            if (c[b] > t) {
+                const double x = a[b] + td;
+                if (GRAD) D[b] = fma(D[b], x, P[b]);
+                P[b] *= x;
+            }
+        }
+    }
+}
+
+// single rising factorial for c <= SMALLC (per-lane loop; used for the "total" term off the table)
+template <bool GRAD>
+__device__ __forceinline__ void rf_one(double a, uint32_t c, double& P, double& D) {
+    P = c >= 1 ? a : 1.0;
+    D = c >= 1 ? 1.0 : 0.0;
+    for (uint32_t t = 1; t < c; ++t) {
+        const double x = a + double(t);
+        if (GRAD) D = fma(D, x, P);
+        P *= x;
+    }
+}
+
+// r[b] = 1 / d[b] with a single division; returns prod d
+__device__ __forceinline__ double inv5(const double (&d)[A1], double (&r)[A1]) {
+    const double p01 = d[0] * d[1], p012 = p01 * d[2], p0123 = p012 * d[3], p = p0123 * d[4];
+    double t = 1.0 / p;
+    r[4] = t * p0123;
+    t *= d[4];
+    r[3] = t * p012;
+    t *= d[3];
+    r[2] = t * p01;
+    t *= d[2];
+    r[1] = t * d[0];
+    r[0] = t * d[1];
+    return p;
 }
 
 // Chunk tables of the linear head.  For chunk ch (positions 4ch..4ch+3) and symbol combination q,
@@ -78,7 +144,8 @@ __device__ __forceinline__ int symbol_at(uint64_t v, int j, int lag, int nstart)
     return j < nstart ? 4 : int((v >> (2 * (lag - 1 - j))) & 3u);
 }
 
-// softmax(sum_j mat[j, s_j, :]); returns false if the fast (chunk-table) path could not be used
+// softmax(sum_j mat[j, s_j, :]) of a start-free k-mer through the chunk tables; false if the ratio
+// product left the double range (the caller then takes the cooperative path)
 __device__ __forceinline__ bool linear_head_fast(const double* R, uint64_t v, int lag, int nch, double (&f)[A1]) {
     double p0 = 1.0, p1 = 1.0, p2 = 1.0, p3 = 1.0;
     for (int ch = 0; ch < nch; ++ch) {
@@ -101,53 +168,163 @@ __device__ __forceinline__ bool linear_head_fast(const double* R, uint64_t v, in
     return true;
 }
 
-__device__ __forceinline__ void linear_head_slow(const double* smat, uint64_t v, int lag, int nstart, double (&f)[A1]) {
-    double l[A1] = {0, 0, 0, 0, 0};
-    for (int j = 0; j < lag; ++j) {
-        const double* row = smat + (j * A1 + symbol_at(v, j, lag, nstart)) * A1;
+// Linear head for one warp tile.  Lanes whose k-mer has start symbols (or whose table product
+// overflowed) are served cooperatively: the warp walks them one at a time, lane j < lag fetches the
+// weight row of position j, and a butterfly sum gives every lane the logits.  Must be called by all 32
+// lanes.  Returns true for lanes that took the chunk-table path (their gradient can be staged by key).
+__device__ __forceinline__ bool linear_head_tile(const double* R, const double* smat, uint64_t code, bool live,
+                                                 int lag, int nch, double (&f)[A1]) {
+    const int lane = threadIdx.x & 31;
+    bool fast = false;
 #pragma unroll
-        for (int b = 0; b < A1; ++b) l[b] += row[b];
+    for (int b = 0; b < A1; ++b) f[b] = 0.2;
+    if (live && (code >> 58) == 0) fast = linear_head_fast(R, code & PAYLOAD_MASK, lag, nch, f);
+    unsigned todo = __ballot_sync(0xffffffffu, live && !fast);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const uint64_t cs = __shfl_sync(0xffffffffu, code, src);
+        double l[A1] = {0, 0, 0, 0, 0};
+        if (lane < lag) {
+            const double* row = smat + (lane * A1 + symbol_at(cs & PAYLOAD_MASK, lane, lag, int(cs >> 58))) * A1;
+#pragma unroll
+            for (int b = 0; b < A1; ++b) l[b] = row[b];
+        }
+#pragma unroll
+        for (int b = 0; b < A1; ++b) l[b] = warp_sum(l[b]);
+        if (lane == src) {
+            double m = l[0];
+#pragma unroll
+            for (int b = 1; b < A1; ++b) m = fmax(m, l[b]);
+            double z = 0.0;
+#pragma unroll
+            for (int b = 0; b < A1; ++b) {
+                f[b] = exp(l[b] - m);
+                z += f[b];
+            }
+            const double zi = 1.0 / z;
+#pragma unroll
+            for (int b = 0; b < A1; ++b) f[b] *= zi;
+        }
     }
-    double m = l[0];
-#pragma unroll
-    for (int b = 1; b < A1; ++b) m = fmax(m, l[b]);
-    double z = 0.0;
-#pragma unroll
-    for (int b = 0; b < A1; ++b) {
-        f[b] = exp(l[b] - m);
-        z += f[b];
-    }
-    const double zi = 1.0 / z;
-#pragma unroll
-    for (int b = 0; b < A1; ++b) f[b] *= zi;
+    return fast;
 }
 
-// Dirichlet-multinomial log-likelihood of one row and d ll / d conc  (core.py:73-74 via TFP's lbeta
-// difference; the add-then-subtract log_combinations term is omitted, it cancels analytically).
+// sum_b [lgamma(conc_b + c_b) - lgamma(conc_b)] = add + log(prod) and, with GRAD, w_b = the digamma
+// differences.  Small counts: predicated rising factorials and one shared division; a lane with a
+// count above SMALLC redoes its row with the general routine (divergent, rare in sparse tables).
 template <bool GRAD>
-__device__ __forceinline__ double dm_row(const double (&conc)[A1], const Row& r, double (&dconc)[A1]) {
-    LogProd num, den;
-    double s = 0.0;
+__device__ __forceinline__ void letters_term(const double (&conc)[A1], const Counts& r, uint32_t steps, double& add,
+                                             double& prod, double (&w)[A1]) {
+    double P[A1], D[A1];
+    rf_letters<GRAD>(conc, r.c, steps, P, D);
+    add = 0.0;
+    if (GRAD) {
+        double ri[A1];
+        prod = inv5(P, ri);
 #pragma unroll
-    for (int b = 0; b < A1; ++b) s += conc[b];
-    const LgDg t = lgdg_diff<GRAD>(s, r.n);
-    den.push(t);
-#pragma unroll
-    for (int b = 0; b < A1; ++b) {
-        const LgDg x = lgdg_diff<GRAD>(conc[b], r.c[b]);
-        num.push(x);
-        if (GRAD) dconc[b] = x.dg - t.dg;
+        for (int b = 0; b < A1; ++b) w[b] = D[b] * ri[b];
+    } else {
+        prod = ((P[0] * P[1]) * (P[2] * P[3])) * P[4];
     }
-    return logprod_diff(num, den);
+    if (r.cmax > SMALLC) {
+        LogProd acc;
+#pragma unroll
+        for (int b = 0; b < A1; ++b) {
+            const LgDg t = lgdg_diff<GRAD>(conc[b], double(r.c[b]));
+            acc.push(t);
+            if (GRAD) w[b] = t.dg;
+        }
+        add = acc.add;
+        prod = acc.mul;
+    }
 }
 
-// Multinomial log-likelihood sum_b c_b log p_b with multiply_no_nan semantics (core.py:138-139)
-__device__ __forceinline__ double mn_row(const double (&p)[A1], const Row& r) {
-    double ll = 0.0;
+// lgamma(s + n) - lgamma(s) = add + log(prod), digamma difference dg
+template <bool GRAD>
+__device__ __forceinline__ void total_term(double s, const Counts& r, double& add, double& prod, double& dg) {
+    if (r.n <= double(SMALLC)) {
+        double D;
+        rf_one<GRAD>(s, uint32_t(r.n), prod, D);
+        add = 0.0;
+        if (GRAD) dg = D / prod;
+    } else {
+        const LgDg t = lgdg_diff<GRAD>(s, r.n);
+        add = t.add;
+        prod = t.mul;
+        if (GRAD) dg = t.dg;
+    }
+}
+
+// sum_b c_b log p_b = add + log(prod)  (multiply_no_nan semantics, core.py:138-139)
+__device__ __forceinline__ void mn_term(const double (&p)[A1], const Counts& r, uint32_t steps, double& add, double& prod) {
+    double pw[A1];
+#pragma unroll
+    for (int b = 0; b < A1; ++b) pw[b] = r.c[b] >= 1 ? p[b] : 1.0;
+    for (uint32_t t = 1; t < steps; ++t) {
+#pragma unroll
+        for (int b = 0; b < A1; ++b)
+            if (r.c[b] > t) pw[b] *= p[b];
+    }
+    add = 0.0;
+    prod = ((pw[0] * pw[1]) * (pw[2] * pw[3])) * pw[4];
+    if (r.cmax > SMALLC) {
+        prod = 1.0;
+#pragma unroll
+        for (int b = 0; b < A1; ++b)
+            if (r.c[b] != 0) add = fma(double(r.c[b]), log(p[b]), add);
+    }
+}
+
+__device__ __forceinline__ double pick5(const uint32_t (&c)[A1], int idx) {
+    const uint32_t v = idx == 0 ? c[0] : idx == 1 ? c[1] : idx == 2 ? c[2] : idx == 3 ? c[3] : c[4];
+    return double(v);
+}
+
+// argmax of v + sigma * N(0,1) (core.py:69-71,134-136).  Candidates are the entries within 16 sigma of
+// the maximum (anything further cannot win, P < 1e-28).  One candidate: no randomness needed.  All
+// candidates exactly tied: a uniform pick, which is what iid noise gives.  Otherwise Gaussian noise on
+// the candidates only.  seed < 0: no noise, first maximum wins.
+__device__ __forceinline__ int noisy_argmax5(const double (&v)[A1], double sigma, int64_t seed, uint64_t row,
+                                             uint64_t model) {
+    int best = 0;
+    double top = v[0];
+#pragma unroll
+    for (int b = 1; b < A1; ++b)
+        if (v[b] > top) {
+            top = v[b];
+            best = b;
+        }
+    if (seed < 0) return best;
+    const double thr = top - 16.0 * sigma;
+    int near = 0, exact = 0;
+#pragma unroll
+    for (int b = 0; b < A1; ++b) {
+        near += v[b] > thr;
+        exact += v[b] == top;
+    }
+    if (near == 1) return best;
+    if (near == exact) {
+        int k = int(rng_u64(uint64_t(seed), row, model * 64 + 63) % uint64_t(exact));
+#pragma unroll
+        for (int b = 0; b < A1; ++b)
+            if (v[b] == top) {
+                if (k == 0) best = b;
+                --k;
+            }
+        return best;
+    }
+    double nb = -INFINITY;
 #pragma unroll
     for (int b = 0; b < A1; ++b)
-        if (r.c[b] != 0.0) ll = fma(r.c[b], log(p[b]), ll);
-    return ll;
+        if (v[b] > thr) {
+            const double x = v[b] + sigma * rng_normal(uint64_t(seed), row, model * 64 + uint64_t(b));
+            if (x > nb) {
+                nb = x;
+                best = b;
+            }
+        }
+    return best;
 }
 
 // Fixed-order second stage: out[p] += mult * sum_blk partials[blk, p]
@@ -163,6 +340,10 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partials, int 
 // ------------------------------------------------------------------------------------------------
 // linear head, fused forward + backward
 // ------------------------------------------------------------------------------------------------
+// Per iteration a CTA handles NW tiles of 32 rows.  Phase A: every warp computes one tile (one row per
+// lane) and stages (k-mer payload, g_0..g_3) -- the gradient w.r.t. the logits -- in shared memory.
+// Phase B: warp ch < nch owns chunk table G[ch]; it walks the NW staged tiles, groups equal chunk keys
+// inside a tile with match.any, and the group leader does a plain read-modify-write.  No atomics.
 template <bool TRAIN_AR>
 __global__ void __launch_bounds__(THREADS, 2)
 linear_train_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ col, int64_t stride,
@@ -170,81 +351,161 @@ linear_train_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restri
                     double* __restrict__ ll_out, double* __restrict__ partials) {
     extern __shared__ __align__(16) double smem[];
     const int nch = num_chunks(lag);
-    double* R = smem;                          // [nch][256][4] forward ratio tables
-    double* G = R + nch * COMBOS * 4;          // [nch][256][4] d ll / d chunk-logits (letters 0..3)
-    double* smat = G + nch * COMBOS * 4;       // [lag][5][5]
-    double* gmat = smat + lag * A1 * A1;       // [lag][5][5]  gradient from slow-path rows
-    double* red = gmat + lag * A1 * A1;        // [32]
+    double* R = smem;                              // [nch][256][4] forward ratio tables
+    double* G = R + nch * COMBOS * 4;              // [nch][256][4] d ll / d chunk-logits (letters 0..3)
+    double* smat = G + nch * COMBOS * 4;           // [lag][5][5]
+    double* gmat = smat + lag * A1 * A1;           // [lag][5][5]  gradient from slow-path rows (rare)
+    double* tab_lg = gmat + lag * A1 * A1;         // [TABN] lgamma(S0 + N) - lgamma(S0)
+    double* tab_dg = tab_lg + TABN;                // [TABN] digamma difference
+    double* red = tab_dg + TABN;                   // [32]
+    double* stage_g = red + 32;                    // [NW][4][32]
+    uint64_t* stage_k = reinterpret_cast<uint64_t*>(stage_g + NW * 4 * 32);   // [NW][32]
 
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double hinv = exp(-h_signed[0]);         // 1 / h,  h = exp(h_signed)  (bear_net.py:186)
     for (int i = threadIdx.x; i < lag * A1 * A1; i += blockDim.x) {
         smat[i] = mat[i];
         gmat[i] = 0.0;
     }
     for (int i = threadIdx.x; i < nch * COMBOS * 4; i += blockDim.x) G[i] = 0.0;
+    if (!TRAIN_AR && threadIdx.x < TABN) {
+        // the concentrations of a row sum to 1/h + 5 eps whatever its k-mer (softmax sums to 1)
+        const LgDg t = lgdg_diff<true>(hinv + A1 * BEAR_EPS, double(threadIdx.x));
+        tab_lg[threadIdx.x] = t.add + (t.mul == 1.0 ? 0.0 : log(t.mul));
+        tab_dg[threadIdx.x] = t.dg;
+    }
     __syncthreads();
     build_ratio_tables(smat, R, lag);
     __syncthreads();
 
-    const double hinv = exp(-h_signed[0]);     // 1 / h,  h = exp(h_signed)  (bear_net.py:186)
-    double ll_sum = 0.0, dh_sum = 0.0;
+    double acc_add = 0.0, dh_sum = 0.0;
+    LogProd acc_prod;
+    const int64_t ntiles = (n + 31) >> 5;
 
-    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
-        const uint64_t code = __ldg(kmers + i);
-        const Row r = load_row(col, stride, i);
-        if (r.n == 0.0) {                      // zero-count row: ll = 0 and every gradient is 0
-            if (ll_out) ll_out[i] = 0.0;
-            continue;
-        }
-        const int nstart = int(code >> 58);
-        const uint64_t v = code & ((1ull << 58) - 1);
-        double f[A1];
-        bool fast = nstart == 0 && linear_head_fast(R, v, lag, nch, f);
-        if (!fast) linear_head_slow(smat, v, lag, nstart, f);
-
-        double ll, df[A1];                     // df = d ll / d f
-        if (TRAIN_AR) {
-            double p[A1];
+    for (int64_t tile0 = int64_t(blockIdx.x) * NW; tile0 < ntiles; tile0 += int64_t(gridDim.x) * NW) {
+        // ---------------- phase A: one row per lane ----------------
+        const int64_t i = ((tile0 + warp) << 5) + lane;
+        const bool in_range = i < n;
+        const uint64_t code = in_range ? __ldg(kmers + i) : 0ull;
+        const Counts r = load_counts(col, stride, i, in_range);
+        const bool live = r.cmax != 0;             // zero-count row: ll = 0 and every gradient is 0
+        const uint32_t steps = warp_steps(live, r.cmax);
+        double f[A1], g[A1] = {0, 0, 0, 0, 0};
+        const bool fast = linear_head_tile(R, smat, code, live, lag, nch, f);
+        double ll_row = 0.0;
+        {
+            double add, prod, w[A1];
+            if (TRAIN_AR) {
+                double p[A1], ri[A1];
 #pragma unroll
-            for (int b = 0; b < A1; ++b) p[b] = f[b] + BEAR_EPS;           // bear_net.py:68
-            ll = mn_row(p, r);
+                for (int b = 0; b < A1; ++b) p[b] = f[b] + BEAR_EPS;                 // bear_net.py:68
+                mn_term(p, r, steps, add, prod);
+                inv5(p, ri);
+                double u = 0.0;
 #pragma unroll
-            for (int b = 0; b < A1; ++b) df[b] = r.c[b] == 0.0 ? 0.0 : r.c[b] / p[b];
-        } else {
-            double conc[A1], dconc[A1];
+                for (int b = 0; b < A1; ++b) {
+                    w[b] = double(r.c[b]) * ri[b];                                   // d ll / d f_b
+                    u = fma(f[b], w[b], u);
+                }
 #pragma unroll
-            for (int b = 0; b < A1; ++b) conc[b] = fma(f[b], hinv, BEAR_EPS);   // bear_net.py:43
-            ll = dm_row<true>(conc, r, dconc);
+                for (int b = 0; b < A1; ++b) g[b] = f[b] * (w[b] - u);
+            } else {
+                double conc[A1];
 #pragma unroll
-            for (int b = 0; b < A1; ++b) df[b] = dconc[b] * hinv;
-        }
-        double u = 0.0;
+                for (int b = 0; b < A1; ++b) conc[b] = fma(f[b], hinv, BEAR_EPS);       // bear_net.py:43
+                letters_term<true>(conc, r, steps, add, prod, w);
+                double tadd, tdg;
+                if (r.n < double(TABN)) {
+                    tadd = tab_lg[int(r.n)];
+                    tdg = tab_dg[int(r.n)];
+                } else {
+                    double tprod;
+                    const double s = ((conc[0] + conc[1]) + (conc[2] + conc[3])) + conc[4];
+                    total_term<true>(s, r, tadd, tprod, tdg);
+                    tadd += log(tprod);
+                }
+                add -= tadd;
+                // d ll/d conc_b = w_b - tdg; d ll/d f_b = that / h; softmax backward:
+                // g_b = f_b (d ll/d f_b - sum_j f_j d ll/d f_j) = f_b (w_b - W) / h,  W = sum_j f_j w_j
+                double W = 0.0;
 #pragma unroll
-        for (int b = 0; b < A1; ++b) u = fma(f[b], df[b], u);
-        ll_sum += ll;
-        if (!TRAIN_AR) dh_sum -= u;            // d ll / d h_signed = -sum_b f_b d ll/d f_b
-        if (ll_out) ll_out[i] = ll;
-
-        double g[A1];                          // softmax backward: d ll / d logits
+                for (int b = 0; b < A1; ++b) W = fma(f[b], w[b], W);
+                if (live) dh_sum -= (W - tdg) * hinv;       // d ll / d h_signed = -sum_b f_b d ll/d f_b
 #pragma unroll
-        for (int b = 0; b < A1; ++b) g[b] = f[b] * (df[b] - u);
-        if (fast) {
-            for (int ch = 0; ch < nch; ++ch) {
-                double* dst = G + (ch * COMBOS + chunk_key(v, ch, nch, lag)) * 4;
-#pragma unroll
-                for (int b = 0; b < 4; ++b) atomicAdd(dst + b, g[b]);
+                for (int b = 0; b < A1; ++b) g[b] = f[b] * hinv * (w[b] - W);
             }
-        } else {
-            for (int j = 0; j < lag; ++j) {
-                double* dst = gmat + (j * A1 + symbol_at(v, j, lag, nstart)) * A1;
-#pragma unroll
-                for (int b = 0; b < A1; ++b) atomicAdd(dst + b, g[b]);
+            if (live) {
+                if (ll_out) {
+                    ll_row = add + log(prod);
+                    acc_add += ll_row;
+                } else {
+                    acc_add += add;
+                    acc_prod.push(0.0, prod);
+                }
             }
         }
+        if (ll_out && in_range) ll_out[i] = ll_row;
+        const uint64_t key = (live && fast) ? (code & PAYLOAD_MASK) : KEY_INVALID;
+        // start-padded k-mers: the warp scatters them position by position (lane j = position j)
+        unsigned todo = __ballot_sync(0xffffffffu, live && !fast);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const uint64_t cs = __shfl_sync(0xffffffffu, code, src);
+            double gs[A1];
+#pragma unroll
+            for (int b = 0; b < A1; ++b) gs[b] = __shfl_sync(0xffffffffu, g[b], src);
+            if (lane < lag) {
+                double* dst = gmat + (lane * A1 + symbol_at(cs & PAYLOAD_MASK, lane, lag, int(cs >> 58))) * A1;
+#pragma unroll
+                for (int b = 0; b < A1; ++b) atomicAdd(dst + b, gs[b]);
+            }
+        }
+        stage_k[warp * 32 + lane] = key;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) stage_g[(warp * 4 + b) * 32 + lane] = g[b];
+        __syncthreads();
+        // ---------------- phase B: warp ch scatters chunk ch of every staged tile ----------------
+        if (warp < nch) {
+            const int ch = warp;
+            double* Gc = G + ch * COMBOS * 4;
+            for (int t = 0; t < NW; ++t) {
+                const uint64_t k = stage_k[t * 32 + lane];
+                const bool valid = k != KEY_INVALID;
+                if (!__any_sync(0xffffffffu, valid)) continue;
+                const int q = valid ? chunk_key(k, ch, nch, lag) : 0x7fffffff;
+                const unsigned grp = __match_any_sync(0xffffffffu, q);
+                if (valid && (__ffs(grp) - 1) == lane) {
+                    const double* sg = stage_g + t * 4 * 32;
+                    double s0 = sg[lane], s1 = sg[32 + lane], s2 = sg[64 + lane], s3 = sg[96 + lane];
+                    unsigned rest = grp & (grp - 1);
+                    while (rest) {
+                        const int j = __ffs(rest) - 1;
+                        rest &= rest - 1;
+                        s0 += sg[j];
+                        s1 += sg[32 + j];
+                        s2 += sg[64 + j];
+                        s3 += sg[96 + j];
+                    }
+                    double2* dst = reinterpret_cast<double2*>(Gc + q * 4);
+                    double2 a = dst[0], b2 = dst[1];
+                    a.x += s0;
+                    a.y += s1;
+                    b2.x += s2;
+                    b2.y += s3;
+                    dst[0] = a;
+                    dst[1] = b2;
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
     }
 
     const int P = 2 + lag * A1 * A1;
     double* out = partials + int64_t(blockIdx.x) * P;
-    const double ll_blk = block_sum(ll_sum, red);
+    const double ll_thread = acc_add + (acc_prod.add + (acc_prod.mul == 1.0 ? 0.0 : log(acc_prod.mul)));
+    const double ll_blk = block_sum(ll_thread, red);
     const double dh_blk = block_sum(dh_sum, red);
     if (threadIdx.x == 0) {
         out[0] = ll_blk;
@@ -283,39 +544,52 @@ explicit_train_kernel(const uint32_t* __restrict__ col, int64_t stride, int64_t 
     __shared__ double red[32];
     const double hinv = exp(-h_signed[0]);
     double ll_sum = 0.0, dh_sum = 0.0;
-    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
-        const Row r = load_row(col, stride, i);
+    // warp-tile loop: every lane of a warp runs the same number of iterations (collectives inside)
+    for (int64_t base = int64_t(blockIdx.x) * blockDim.x; base < n; base += int64_t(gridDim.x) * blockDim.x) {
+        const int64_t i = base + threadIdx.x;
+        const bool in_range = i < n;
+        const Counts r = load_counts(col, stride, i, in_range);
+        const bool live = r.cmax != 0;
+        const uint32_t steps = warp_steps(live, r.cmax);
         double f[A1], df[A1], ll = 0.0;
 #pragma unroll
         for (int b = 0; b < A1; ++b) {
-            f[b] = f_in[i * A1 + b];
+            f[b] = in_range ? f_in[i * A1 + b] : 0.2;
             df[b] = 0.0;
         }
-        if (r.n != 0.0) {
-            if (TRAIN_AR) {
-                double p[A1];
+        double add, prod, w[A1];
+        if (TRAIN_AR) {
+            double p[A1];
 #pragma unroll
-                for (int b = 0; b < A1; ++b) p[b] = f[b] + BEAR_EPS;
-                ll = mn_row(p, r);
+            for (int b = 0; b < A1; ++b) p[b] = f[b] + BEAR_EPS;
+            mn_term(p, r, steps, add, prod);
 #pragma unroll
-                for (int b = 0; b < A1; ++b) df[b] = r.c[b] == 0.0 ? 0.0 : r.c[b] / p[b];
-            } else {
-                double conc[A1], dconc[A1];
+            for (int b = 0; b < A1; ++b) df[b] = r.c[b] == 0 ? 0.0 : double(r.c[b]) / p[b];
+        } else {
+            double conc[A1], tadd, tprod, tdg;
 #pragma unroll
-                for (int b = 0; b < A1; ++b) conc[b] = fma(f[b], hinv, BEAR_EPS);
-                ll = dm_row<true>(conc, r, dconc);
+            for (int b = 0; b < A1; ++b) conc[b] = fma(f[b], hinv, BEAR_EPS);
+            letters_term<true>(conc, r, steps, add, prod, w);
+            const double s = ((conc[0] + conc[1]) + (conc[2] + conc[3])) + conc[4];
+            total_term<true>(s, r, tadd, tprod, tdg);
+            add -= tadd;
+            prod /= tprod;
+            if (live) {
 #pragma unroll
                 for (int b = 0; b < A1; ++b) {
-                    df[b] = dconc[b] * hinv;
+                    df[b] = (w[b] - tdg) * hinv;
                     dh_sum -= f[b] * df[b];
                 }
             }
         }
+        if (live) ll = add + log(prod);
         ll_sum += ll;
-        if (ll_out) ll_out[i] = ll;
-        if (gf) {
+        if (in_range) {
+            if (ll_out) ll_out[i] = ll;
+            if (gf) {
 #pragma unroll
-            for (int b = 0; b < A1; ++b) gf[i * A1 + b] = -scale * df[b];
+                for (int b = 0; b < A1; ++b) gf[i * A1 + b] = -scale * df[b];
+            }
         }
     }
     const double ll_blk = block_sum(ll_sum, red);
@@ -329,98 +603,177 @@ explicit_train_kernel(const uint32_t* __restrict__ col, int64_t stride, int64_t 
 // ------------------------------------------------------------------------------------------------
 // evaluation
 // ------------------------------------------------------------------------------------------------
-struct EvalParams {
-    double h[BEAR_MAX_MODELS];
-    double van[BEAR_MAX_MODELS];
-    int H, V;
-};
-
-template <int HEAD>
-__global__ void __launch_bounds__(THREADS, 1)
+// NM bounds both the number of h values (H) and of BMM priors (V) of one launch.
+template <int HEAD, int NM, bool HAS_TRAIN>
+__global__ void __launch_bounds__(THREADS, 2)
 eval_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ test_col,
             const uint32_t* __restrict__ train_col, int64_t stride, int64_t row0, int64_t n, int lag,
             const double* __restrict__ head, const double* __restrict__ d_h, int H,
             const double* __restrict__ d_van, int V, int64_t seed, double* __restrict__ partials) {
     extern __shared__ __align__(16) double smem[];
     const int nch = num_chunks(lag);
+    constexpr bool LIN = HEAD == BEAR_HEAD_LINEAR;
+    // the sum of a row's BEAR concentrations is row-independent when there is no conditioning column
+    // and the head is normalised (or absent)
+    constexpr bool TOT_TAB = !HAS_TRAIN && HEAD != BEAR_HEAD_EXPLICIT;
     double* R = smem;
-    double* smat = R + (HEAD == BEAR_HEAD_LINEAR ? nch * COMBOS * 4 : 0);
-    double* red = smat + (HEAD == BEAR_HEAD_LINEAR ? lag * A1 * A1 : 0);
-    if (HEAD == BEAR_HEAD_LINEAR) {
+    double* smat = R + (LIN ? nch * COMBOS * 4 : 0);
+    double* red = smat + (LIN ? lag * A1 * A1 : 0);
+    double* tab_ear = red + 32;                    // [NM][TABN]  lgamma(S0_k + N) - lgamma(S0_k)
+    double* tab_van = tab_ear + NM * TABN;         // [NM][TABN]  lgamma(van_k + eps + c) - lgamma(van_k + eps)
+    double* tab_vtot = tab_van + NM * TABN;        // [NM][TABN]  lgamma(5 (van_k + eps) + N) - lgamma(5 (van_k + eps))
+    if (LIN) {
         for (int i = threadIdx.x; i < lag * A1 * A1; i += blockDim.x) smat[i] = head[i];
         __syncthreads();
         build_ratio_tables(smat, R, lag);
-        __syncthreads();
     }
-    double hinv[BEAR_MAX_MODELS], van[BEAR_MAX_MODELS];
+    double hinv[NM], van[NM];
 #pragma unroll
-    for (int k = 0; k < BEAR_MAX_MODELS; ++k) {
-        hinv[k] = k < H ? 1.0 / d_h[k] : 0.0;
-        van[k] = k < V ? d_van[k] : 0.0;
+    for (int k = 0; k < NM; ++k) {
+        hinv[k] = k < H ? 1.0 / d_h[k] : 1.0;
+        van[k] = k < V ? d_van[k] : 1.0;
     }
-    double ll_ear[BEAR_MAX_MODELS], cor_ear[BEAR_MAX_MODELS], ll_van[BEAR_MAX_MODELS], cor_van[BEAR_MAX_MODELS];
-#pragma unroll
-    for (int k = 0; k < BEAR_MAX_MODELS; ++k) ll_ear[k] = cor_ear[k] = ll_van[k] = cor_van[k] = 0.0;
-    double ll_arm = 0.0, cor_arm = 0.0, total = 0.0;
+    if (!HAS_TRAIN) {
+        for (int idx = threadIdx.x; idx < NM * TABN; idx += blockDim.x) {
+            const int k = idx / TABN;
+            const double c = double(idx % TABN);
+            const double hk = k < H ? 1.0 / d_h[k] : 1.0, vk = (k < V ? d_van[k] : 1.0) + BEAR_EPS;
+            const double s0 = (HEAD == BEAR_HEAD_NONE ? 0.0 : hk) + A1 * BEAR_EPS;
+            LgDg t = lgdg_diff<false>(s0, c);
+            tab_ear[idx] = t.add + (t.mul == 1.0 ? 0.0 : log(t.mul));
+            t = lgdg_diff<false>(vk, c);
+            tab_van[idx] = t.add + (t.mul == 1.0 ? 0.0 : log(t.mul));
+            t = lgdg_diff<false>(double(A1) * vk, c);
+            tab_vtot[idx] = t.add + (t.mul == 1.0 ? 0.0 : log(t.mul));
+        }
+    }
+    __syncthreads();
 
-    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
-        const Row r = load_row(test_col, stride, i);
-        if (r.n == 0.0) continue;              // no test transitions: contributes 0 to every output
+    double ear_add[NM], cor_ear[NM], van_add[NM], cor_van[NM];
+    LogProd ear_prod[NM];
+#pragma unroll
+    for (int k = 0; k < NM; ++k) ear_add[k] = cor_ear[k] = van_add[k] = cor_van[k] = 0.0;
+    double arm_add = 0.0, cor_arm = 0.0, total = 0.0;
+    LogProd arm_prod;
+
+    for (int64_t base = int64_t(blockIdx.x) * blockDim.x; base < n; base += int64_t(gridDim.x) * blockDim.x) {
+        const int64_t i = base + threadIdx.x;
+        const bool in_range = i < n;
+        const Counts r = load_counts(test_col, stride, i, in_range);
+        const bool live = r.cmax != 0;             // no test transitions: contributes 0 to every output
+        const uint32_t steps = warp_steps(live, r.cmax);
         double t[A1] = {0, 0, 0, 0, 0};
-        if (train_col) {
+        if (HAS_TRAIN && live) {
 #pragma unroll
             for (int b = 0; b < A1; ++b) t[b] = double(__ldg(train_col + b * stride + i));
         }
-        double f[A1] = {0, 0, 0, 0, 0};
-        if (HEAD == BEAR_HEAD_LINEAR) {
-            const uint64_t code = __ldg(kmers + i);
-            const int nstart = int(code >> 58);
-            const uint64_t v = code & ((1ull << 58) - 1);
-            if (!(nstart == 0 && linear_head_fast(R, v, lag, nch, f))) linear_head_slow(smat, v, lag, nstart, f);
-        } else if (HEAD == BEAR_HEAD_EXPLICIT) {
+        double f[A1];
+        if (LIN) {
+            linear_head_tile(R, smat, in_range ? __ldg(kmers + i) : 0ull, live, lag, nch, f);
+        } else {
 #pragma unroll
-            for (int b = 0; b < A1; ++b) f[b] = head[i * A1 + b];
-        } else if (HEAD == BEAR_HEAD_STOP) {
-            f[A1 - 1] = 1.0;
+            for (int b = 0; b < A1; ++b)
+                f[b] = HEAD == BEAR_HEAD_EXPLICIT ? (in_range ? head[i * A1 + b] : 0.2)
+                                                  : ((HEAD == BEAR_HEAD_STOP && b == A1 - 1) ? 1.0 : 0.0);
         }
         total += r.n;
         const uint64_t grow = uint64_t(row0 + i);
+        const bool use_tab = !HAS_TRAIN && r.n < double(TABN);
         double dummy[A1];
         // BEAR: conc = f / h + train + eps   (bear_net.py:43, 335-337)
-        for (int k = 0; k < H; ++k) {
-            double conc[A1];
 #pragma unroll
-            for (int b = 0; b < A1; ++b) conc[b] = fma(f[b], hinv[k], t[b]) + BEAR_EPS;
-            ll_ear[k] += dm_row<false>(conc, r, dummy);
-            cor_ear[k] += r.c[noisy_argmax<A1>(conc, 100.0 * BEAR_EPS, seed, grow, uint64_t(k))];
+        for (int k = 0; k < NM; ++k) {
+            if (k < H) {
+                double conc[A1], add, prod;
+#pragma unroll
+                for (int b = 0; b < A1; ++b) conc[b] = fma(f[b], hinv[k], t[b]) + BEAR_EPS;
+                letters_term<false>(conc, r, steps, add, prod, dummy);
+                if (TOT_TAB && use_tab) {
+                    add -= tab_ear[k * TABN + int(r.n)];
+                } else {
+                    double tadd, tprod, tdg;
+                    const double s = ((conc[0] + conc[1]) + (conc[2] + conc[3])) + conc[4];
+                    total_term<false>(s, r, tadd, tprod, tdg);
+                    add -= tadd;
+                    prod /= tprod;
+                }
+                if (live) {
+                    ear_add[k] += add;
+                    ear_prod[k].push(0.0, prod);
+                    cor_ear[k] += pick5(r.c, noisy_argmax5(conc, 100.0 * BEAR_EPS, seed, grow, uint64_t(k)));
+                }
+            }
         }
         // AR: p = f + eps   (bear_net.py:68, 338)
         {
-            double p[A1];
+            double p[A1], add, prod;
 #pragma unroll
             for (int b = 0; b < A1; ++b) p[b] = f[b] + BEAR_EPS;
-            ll_arm += mn_row(p, r);
-            cor_arm += r.c[noisy_argmax<A1>(p, BEAR_EPS, seed, grow, 100)];
+            mn_term(p, r, steps, add, prod);
+            if (live) {
+                arm_add += add;
+                arm_prod.push(0.0, prod);
+                cor_arm += pick5(r.c, noisy_argmax5(p, BEAR_EPS, seed, grow, 100));
+            }
         }
         // vanilla BMM: conc = train + van + eps   (bear_net.py:328-331, 339-340)
-        for (int k = 0; k < V; ++k) {
-            double conc[A1];
 #pragma unroll
-            for (int b = 0; b < A1; ++b) conc[b] = (t[b] + van[k]) + BEAR_EPS;
-            ll_van[k] += dm_row<false>(conc, r, dummy);
-            cor_van[k] += r.c[noisy_argmax<A1>(conc, 100.0 * BEAR_EPS, seed, grow, 200 + uint64_t(k))];
+        for (int k = 0; k < NM; ++k) {
+            if (k < V) {
+                double conc[A1];
+#pragma unroll
+                for (int b = 0; b < A1; ++b) conc[b] = (t[b] + van[k]) + BEAR_EPS;
+                if (!HAS_TRAIN) {
+                    if (use_tab) {
+                        const double* tv = tab_van + k * TABN;
+                        van_add[k] += (((tv[r.c[0]] + tv[r.c[1]]) + (tv[r.c[2]] + tv[r.c[3]])) + tv[r.c[4]]) -
+                                      tab_vtot[k * TABN + int(r.n)];
+                    } else {
+                        LogProd num, den;
+                        den.push(lgdg_diff<false>(((conc[0] + conc[1]) + (conc[2] + conc[3])) + conc[4], r.n));
+#pragma unroll
+                        for (int b = 0; b < A1; ++b) num.push(lgdg_diff<false>(conc[b], double(r.c[b])));
+                        van_add[k] += logprod_diff(num, den);
+                    }
+                } else {
+                    double add, prod, tadd, tprod, tdg;
+                    letters_term<false>(conc, r, steps, add, prod, dummy);
+                    const double s = ((conc[0] + conc[1]) + (conc[2] + conc[3])) + conc[4];
+                    total_term<false>(s, r, tadd, tprod, tdg);
+                    if (live) van_add[k] += (add - tadd) + log(prod / tprod);
+                }
+                if (live) cor_van[k] += pick5(r.c, noisy_argmax5(conc, 100.0 * BEAR_EPS, seed, grow, 200 + uint64_t(k)));
+            }
         }
     }
     // layout: [ll_ear[H], ll_arm, ll_van[V], cor_ear[H], cor_arm, cor_van[V], total]
     const int P = 2 * H + 2 * V + 3;
     double* out = partials + int64_t(blockIdx.x) * P;
     int o = 0;
-    for (int k = 0; k < H; ++k, ++o) { const double s = block_sum(ll_ear[k], red); if (threadIdx.x == 0) out[o] = s; }
-    { const double s = block_sum(ll_arm, red); if (threadIdx.x == 0) out[o] = s; ++o; }
-    for (int k = 0; k < V; ++k, ++o) { const double s = block_sum(ll_van[k], red); if (threadIdx.x == 0) out[o] = s; }
-    for (int k = 0; k < H; ++k, ++o) { const double s = block_sum(cor_ear[k], red); if (threadIdx.x == 0) out[o] = s; }
+#pragma unroll
+    for (int k = 0; k < NM; ++k)
+        if (k < H) {
+            const double v = ear_add[k] + (ear_prod[k].add + (ear_prod[k].mul == 1.0 ? 0.0 : log(ear_prod[k].mul)));
+            const double s = block_sum(v, red);
+            if (threadIdx.x == 0) out[o] = s;
+            ++o;
+        }
+    {
+        const double v = arm_add + (arm_prod.add + (arm_prod.mul == 1.0 ? 0.0 : log(arm_prod.mul)));
+        const double s = block_sum(v, red);
+        if (threadIdx.x == 0) out[o] = s;
+        ++o;
+    }
+#pragma unroll
+    for (int k = 0; k < NM; ++k)
+        if (k < V) { const double s = block_sum(van_add[k], red); if (threadIdx.x == 0) out[o] = s; ++o; }
+#pragma unroll
+    for (int k = 0; k < NM; ++k)
+        if (k < H) { const double s = block_sum(cor_ear[k], red); if (threadIdx.x == 0) out[o] = s; ++o; }
     { const double s = block_sum(cor_arm, red); if (threadIdx.x == 0) out[o] = s; ++o; }
-    for (int k = 0; k < V; ++k, ++o) { const double s = block_sum(cor_van[k], red); if (threadIdx.x == 0) out[o] = s; }
+#pragma unroll
+    for (int k = 0; k < NM; ++k)
+        if (k < V) { const double s = block_sum(cor_van[k], red); if (threadIdx.x == 0) out[o] = s; ++o; }
     { const double s = block_sum(total, red); if (threadIdx.x == 0) out[o] = s; }
 }
 
@@ -432,6 +785,8 @@ __global__ void __launch_bounds__(THREADS)
 bmm_kernel(const uint32_t* __restrict__ counts, int64_t stride, int64_t n, int G,
            const double* __restrict__ d_alpha, int V, double* __restrict__ partials) {
     __shared__ double red[32];
+    __shared__ double tab[BEAR_MAX_MODELS][TABN];      // lgamma(a + c) - lgamma(a)
+    __shared__ double tab_tot[BEAR_MAX_MODELS][TABN];  // lgamma(A1 a + N) - lgamma(A1 a)
     const int g = blockIdx.y;
     const uint32_t* col = counts + int64_t(g) * NA1 * stride;
     double alpha[BEAR_MAX_MODELS], acc[BEAR_MAX_MODELS];
@@ -440,20 +795,43 @@ bmm_kernel(const uint32_t* __restrict__ counts, int64_t stride, int64_t n, int G
         alpha[k] = k < V ? d_alpha[k] : 1.0;
         acc[k] = 0.0;
     }
+    for (int idx = threadIdx.x; idx < BEAR_MAX_MODELS * TABN; idx += blockDim.x) {
+        const int k = idx / TABN;
+        const double a = k < V ? d_alpha[k] : 1.0, c = double(idx % TABN);
+        LgDg t = lgdg_diff<false>(a, c);
+        tab[k][idx % TABN] = t.add + (t.mul == 1.0 ? 0.0 : log(t.mul));
+        t = lgdg_diff<false>(double(NA1) * a, c);
+        tab_tot[k][idx % TABN] = t.add + (t.mul == 1.0 ? 0.0 : log(t.mul));
+    }
+    __syncthreads();
     for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
-        double c[NA1], tot = 0.0;
+        uint32_t c[NA1], cmax = 0;
+        double tot = 0.0;
 #pragma unroll
         for (int b = 0; b < NA1; ++b) {
-            c[b] = double(__ldg(col + b * stride + i));
-            tot += c[b];
+            c[b] = __ldg(col + b * stride + i);
+            cmax = max(cmax, c[b]);
+            tot += double(c[b]);
         }
-        if (tot == 0.0) continue;
-        for (int k = 0; k < V; ++k) {
-            LogProd num, den;
-            den.push(lgdg_diff<false>(double(NA1) * alpha[k], tot));
+        if (cmax == 0) continue;
+        if (tot < double(TABN)) {
 #pragma unroll
-            for (int b = 0; b < NA1; ++b) num.push(lgdg_diff<false>(alpha[k], c[b]));
-            acc[k] += logprod_diff(num, den);
+            for (int k = 0; k < BEAR_MAX_MODELS; ++k) {
+                if (k < V) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int b = 0; b < NA1; ++b) s += tab[k][c[b]];
+                    acc[k] += s - tab_tot[k][int(tot)];
+                }
+            }
+        } else {
+            for (int k = 0; k < V; ++k) {
+                LogProd num, den;
+                den.push(lgdg_diff<false>(double(NA1) * alpha[k], tot));
+#pragma unroll
+                for (int b = 0; b < NA1; ++b) num.push(lgdg_diff<false>(alpha[k], double(c[b])));
+                acc[k] += logprod_diff(num, den);
+            }
         }
     }
     for (int k = 0; k < V; ++k) {
@@ -462,18 +840,19 @@ bmm_kernel(const uint32_t* __restrict__ counts, int64_t stride, int64_t n, int G
     }
 }
 
-int grid_for(int64_t n) {
+int grid_for(int64_t n, int cap = MAX_GRID) {
     int64_t blocks = (n + THREADS - 1) / THREADS;
     if (blocks < 1) blocks = 1;
-    return int(blocks < MAX_GRID ? blocks : MAX_GRID);
+    return int(blocks < cap ? blocks : cap);
 }
 
 size_t train_smem_bytes(int lag) {
-    return sizeof(double) * (size_t(num_chunks(lag)) * COMBOS * 4 * 2 + size_t(lag) * A1 * A1 * 2 + 32);
+    return sizeof(double) * (size_t(num_chunks(lag)) * COMBOS * 4 * 2 + size_t(lag) * A1 * A1 * 2 + 2 * TABN + 32 +
+                             NW * 4 * 32 + NW * 32);
 }
 
-size_t eval_smem_bytes(int head, int lag) {
-    size_t d = 32;
+size_t eval_smem_bytes(int head, int lag, int nm) {
+    size_t d = 32 + size_t(3) * nm * TABN;
     if (head == BEAR_HEAD_LINEAR) d += size_t(num_chunks(lag)) * COMBOS * 4 + size_t(lag) * A1 * A1;
     return sizeof(double) * d;
 }
@@ -484,6 +863,33 @@ int set_smem(K kernel, size_t bytes) {
         BEAR_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes)));
     }
     return 0;
+}
+
+template <int HEAD, int NM, bool HAS_TRAIN>
+int launch_eval(int grid, size_t smem, cudaStream_t st, const uint64_t* km, const uint32_t* te, const uint32_t* tr,
+                int64_t stride, int64_t row0, int64_t n, int lag, const double* head, const double* d_h, int H,
+                const double* d_van, int V, int64_t seed, double* ws) {
+    if (set_smem(eval_kernel<HEAD, NM, HAS_TRAIN>, smem)) return BEAR_ERR_CUDA;
+    eval_kernel<HEAD, NM, HAS_TRAIN><<<grid, THREADS, smem, st>>>(km, te, tr, stride, row0, n, lag, head, d_h, H, d_van, V,
+                                                                  seed, ws);
+    return 0;
+}
+
+template <int HEAD, int NM>
+int launch_eval_t(bool has_train, int grid, size_t smem, cudaStream_t st, const uint64_t* km, const uint32_t* te,
+                  const uint32_t* tr, int64_t stride, int64_t row0, int64_t n, int lag, const double* head,
+                  const double* d_h, int H, const double* d_van, int V, int64_t seed, double* ws) {
+    return has_train ? launch_eval<HEAD, NM, true>(grid, smem, st, km, te, tr, stride, row0, n, lag, head, d_h, H, d_van, V, seed, ws)
+                     : launch_eval<HEAD, NM, false>(grid, smem, st, km, te, tr, stride, row0, n, lag, head, d_h, H, d_van, V, seed, ws);
+}
+
+template <int HEAD>
+int launch_eval_nm(int nm, bool has_train, int grid, size_t smem, cudaStream_t st, const uint64_t* km, const uint32_t* te,
+                   const uint32_t* tr, int64_t stride, int64_t row0, int64_t n, int lag, const double* head,
+                   const double* d_h, int H, const double* d_van, int V, int64_t seed, double* ws) {
+    if (nm <= 1) return launch_eval_t<HEAD, 1>(has_train, grid, smem, st, km, te, tr, stride, row0, n, lag, head, d_h, H, d_van, V, seed, ws);
+    if (nm <= 4) return launch_eval_t<HEAD, 4>(has_train, grid, smem, st, km, te, tr, stride, row0, n, lag, head, d_h, H, d_van, V, seed, ws);
+    return launch_eval_t<HEAD, 8>(has_train, grid, smem, st, km, te, tr, stride, row0, n, lag, head, d_h, H, d_van, V, seed, ws);
 }
 
 }  // namespace
@@ -506,7 +912,7 @@ extern "C" int bear_linear_train_step(const uint64_t* d_kmers, const uint32_t* d
     BEAR_REQUIRE(lag >= 1 && lag <= 29, fn);
     if (n == 0) return BEAR_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int grid = grid_for(n);
+    const int grid = grid_for(n, 148 * 2);
     const size_t smem = train_smem_bytes(lag);
     const int P = 2 + lag * A1 * A1;
     if (train_ar) {
@@ -558,23 +964,22 @@ extern "C" int bear_eval_step(const uint64_t* d_kmers, const uint32_t* d_test_co
     if (head == BEAR_HEAD_EXPLICIT) BEAR_REQUIRE(d_head != nullptr, fn);
     if (n == 0) return BEAR_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int grid = grid_for(n);
-    const size_t smem = eval_smem_bytes(head, lag);
+    const int grid = grid_for(n, 148 * 2);
+    const int nm = H > V ? H : V;
+    const int nmt = nm <= 1 ? 1 : nm <= 4 ? 4 : 8;
+    const size_t smem = eval_smem_bytes(head, lag, nmt);
     const uint64_t* km = d_kmers ? d_kmers + row0 : nullptr;
     const uint32_t* tr = d_train_col ? d_train_col + row0 : nullptr;
-#define BEAR_EVAL_LAUNCH(HEADV, HEADPTR)                                                                       \
-    do {                                                                                                       \
-        if (set_smem(eval_kernel<HEADV>, smem)) return BEAR_ERR_CUDA;                                          \
-        eval_kernel<HEADV><<<grid, THREADS, smem, st>>>(km, d_test_col + row0, tr, stride, row0, n, lag,       \
-                                                        HEADPTR, d_h, H, d_van, V, seed, d_workspace);         \
-    } while (0)
+    const uint32_t* te = d_test_col + row0;
+    const bool ht = tr != nullptr;
+    int rc;
     switch (head) {
-        case BEAR_HEAD_LINEAR: BEAR_EVAL_LAUNCH(BEAR_HEAD_LINEAR, d_head); break;
-        case BEAR_HEAD_EXPLICIT: BEAR_EVAL_LAUNCH(BEAR_HEAD_EXPLICIT, d_head); break;
-        case BEAR_HEAD_STOP: BEAR_EVAL_LAUNCH(BEAR_HEAD_STOP, d_head); break;
-        default: BEAR_EVAL_LAUNCH(BEAR_HEAD_NONE, d_head); break;
+        case BEAR_HEAD_LINEAR: rc = launch_eval_nm<BEAR_HEAD_LINEAR>(nm, ht, grid, smem, st, km, te, tr, stride, row0, n, lag, d_head, d_h, H, d_van, V, seed, d_workspace); break;
+        case BEAR_HEAD_EXPLICIT: rc = launch_eval_nm<BEAR_HEAD_EXPLICIT>(nm, ht, grid, smem, st, km, te, tr, stride, row0, n, lag, d_head, d_h, H, d_van, V, seed, d_workspace); break;
+        case BEAR_HEAD_STOP: rc = launch_eval_nm<BEAR_HEAD_STOP>(nm, ht, grid, smem, st, km, te, tr, stride, row0, n, lag, d_head, d_h, H, d_van, V, seed, d_workspace); break;
+        default: rc = launch_eval_nm<BEAR_HEAD_NONE>(nm, ht, grid, smem, st, km, te, tr, stride, row0, n, lag, d_head, d_h, H, d_van, V, seed, d_workspace); break;
     }
-#undef BEAR_EVAL_LAUNCH
+    if (rc) return rc;
     BEAR_LAUNCH_CHECK("eval_kernel");
     const int P = 2 * H + 2 * V + 3;
     reduce_partials_kernel<<<1, 64, 0, st>>>(d_workspace, grid, P, 1.0, d_acc);
