@@ -51,7 +51,7 @@ struct LgDg {
 };
 
 template <bool GRAD>
-__device__ __forceinline__ LgDg lgdg_diff(double a, double c) {
+__device__ __noinline__ LgDg lgdg_diff(double a, double c) {
     LgDg r;
     r.add = 0.0;
     r.mul = 1.0;
@@ -173,7 +173,7 @@ __device__ __forceinline__ double u01(uint64_t bits) {
     return (double(bits >> 11) + 0.5) * (1.0 / 9007199254740992.0);
 }
 
-__device__ __forceinline__ double rng_normal(uint64_t seed, uint64_t a, uint64_t b) {
+static __device__ __noinline__ double rng_normal(uint64_t seed, uint64_t a, uint64_t b) {
     const uint64_t x = rng_u64(seed, a, b);
     const double u1 = u01(x), u2 = u01(mix64(x));
     return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);

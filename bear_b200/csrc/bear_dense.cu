@@ -201,7 +201,7 @@ __global__ void log_normalize_kernel(double* __restrict__ x, int64_t groups, int
 
 // Deterministic synthetic table (bench / large-scale parity): every cell is a pure function of
 // (seed, global row index), so any shard of any size regenerates the same rows.
-//   k-mer : code = (row * ODD + OFFSET) mod 4^lag -- a bijection of the row index, pseudo-random
+//   k-mer : a hash bijection of the row index on [0, 4^lag) -- distinct k-mers in pseudo-random
 //           order (the reference recommends shuffled tables, docs/usage.rst:191-194); a
 //           start_permille/1000 slice gets a start-padded prefix.
 //   counts: regime 0 "sparse": N = 1 + Poisson(2) transitions, each to the row's dominant letter
@@ -214,7 +214,15 @@ __global__ void synth_table_kernel(uint64_t* __restrict__ kmers, uint32_t* __res
     const uint64_t mask = lag >= 29 ? ((1ull << 58) - 1) : ((1ull << (2 * lag)) - 1);
     for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
         const uint64_t row = uint64_t(row_begin + i);
-        uint64_t code = (row * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull * uint64_t(seed + 1)) & mask;
+        // bijection of the row index on [0, 4^lag): odd multiply / xor-shift rounds, each invertible mod 2^(2 lag)
+        const int bits = lag >= 29 ? 58 : 2 * lag;
+        uint64_t code = (row + 0x632BE59BD9B4E019ull * uint64_t(seed + 1)) & mask;
+        for (int round = 0; round < 3; ++round) {
+            code = (code * 0x9E3779B97F4A7C15ull) & mask;
+            code ^= code >> (bits / 2 + 1);
+            code = (code * 0xD1B54A32D192ED03ull) & mask;
+            code ^= code >> (bits / 3 + 1);
+        }
         const uint64_t hs = rng_u64(uint64_t(seed), row, 1);
         if (int(hs % 1000) < start_permille) {
             const uint64_t ns = 1 + (hs >> 20) % uint64_t(lag);

@@ -13,7 +13,7 @@
 //   * log() is taken of running products spanning many rows, not once per row; the five reciprocals
 //     of a row share one division;
 //   * the weight-table gradient is scattered without atomics: rows are staged in shared memory and
-//     each chunk table is owned by one warp, which resolves intra-tile collisions with match.any.
+//     each chunk table is owned by one warp, which serialises intra-tile key collisions through a tag array.
 // Reductions are two-stage and deterministic across CTAs: per-CTA partials in the caller's workspace,
 // then a fixed-order sum.
 #include <math.h>
@@ -27,21 +27,26 @@ namespace {
 using namespace bear;
 
 constexpr int A1 = 5;            // DNA/RNA letters + stop
-constexpr int CHUNK = 4;         // positions per chunk table
+constexpr int CHUNK = 4;         // positions per forward chunk table (ratio tables R)
 constexpr int COMBOS = 256;      // 4^CHUNK
+constexpr int GCHUNK = 4;        // positions per gradient chunk table (G)
+constexpr int GCOMBOS = 256;     // 4^GCHUNK
 constexpr int THREADS = 256;
 constexpr int NW = THREADS / 32;
 constexpr int MAX_GRID = 148 * 4;
 constexpr int TABN = 64;         // counts below TABN index the per-CTA tables of row-independent terms
 constexpr uint64_t PAYLOAD_MASK = (1ull << 58) - 1;
 constexpr uint64_t KEY_INVALID = ~0ull;
+constexpr int SLOWCAP = 8;       // start-padded rows per tile that are staged (more fall back to atomics)
 
 __host__ __device__ inline int num_chunks(int lag) { return (lag + CHUNK - 1) / CHUNK; }
+__host__ __device__ inline int num_gchunks(int lag) { return (lag + GCHUNK - 1) / GCHUNK; }
 
 // ------------------------------------------------------------------------------------------------
 // per-row pieces
 // ------------------------------------------------------------------------------------------------
-constexpr uint32_t SMALLC = 8;   // counts up to SMALLC take the predicated rising-factorial path
+constexpr uint32_t SMALLC = 8;   // counts up to SMALLC take the polynomial rising-factorial path
+constexpr int STIR_N = (SMALLC + 1) * (SMALLC + 1) + 1;   // padded to keep 16-byte alignment after it
 
 struct Counts {
     uint32_t c[A1];
@@ -63,25 +68,37 @@ __device__ __forceinline__ uint32_t warp_steps(bool live, uint32_t cmax) {
     return __reduce_max_sync(0xffffffffu, live ? (cmax < SMALLC ? cmax : SMALLC) : 0u);
 }
 
-// Rising factorials P_b = prod_{i<c_b}(a_b + i) and derivatives D_b for the five letters of a row.
-// `steps` is warp-uniform, the body predicated: no divergence.  Valid for c_b <= SMALLC.
+// Rising factorials P_b = prod_{i<c_b}(a_b + i) and derivatives D_b = dP_b/da for the five letters of a
+// row with counts <= SMALLC, as polynomials in a: P_c(a) = sum_k S(c,k) a^k with the unsigned Stirling
+// numbers of the first kind (all terms positive for a > 0, so Horner is well conditioned).  `steps` is
+// the warp-wide largest count, so the degree loop is divergence-free; the coefficient row is picked per
+// lane and letter from a shared-memory copy of the triangle.
+__constant__ double kStirling[(SMALLC + 1) * (SMALLC + 1)] = {
+    1, 0, 0, 0, 0, 0, 0, 0, 0,
+    0, 1, 0, 0, 0, 0, 0, 0, 0,
+    0, 1, 1, 0, 0, 0, 0, 0, 0,
+    0, 2, 3, 1, 0, 0, 0, 0, 0,
+    0, 6, 11, 6, 1, 0, 0, 0, 0,
+    0, 24, 50, 35, 10, 1, 0, 0, 0,
+    0, 120, 274, 225, 85, 15, 1, 0, 0,
+    0, 720, 1764, 1624, 735, 175, 21, 1, 0,
+    0, 5040, 13068, 13132, 6769, 1960, 322, 28, 1};
+
 template <bool GRAD>
-__device__ __forceinline__ void rf_letters(const double (&a)[A1], const uint32_t (&c)[A1], uint32_t steps,
-                                           double (&P)[A1], double (&D)[A1]) {
+__device__ __forceinline__ void rf_letters(const double* __restrict__ stir, const double (&a)[A1], const uint32_t (&c)[A1],
+                                           uint32_t steps, double (&P)[A1], double (&D)[A1]) {
+    const double* row[A1];
 #pragma unroll
     for (int b = 0; b < A1; ++b) {
-        P[b] = c[b] >= 1 ? a[b] : 1.0;
-        D[b] = c[b] >= 1 ? 1.0 : 0.0;
+        row[b] = stir + (c[b] <= SMALLC ? c[b] : 0u) * (SMALLC + 1);
+        P[b] = row[b][steps];
+        D[b] = 0.0;
     }
-    for (uint32_t t = 1; t < steps; ++t) {
-        const double td = double(t);
+    for (int k = int(steps) - 1; k >= 0; --k) {
 #pragma unroll
         for (int b = 0; b < A1; ++b) {
-            if (c[b] > t) {
-                const double x = a[b] + td;
-                if (GRAD) D[b] = fma(D[b], x, P[b]);
-                P[b] *= x;
-            }
+            if (GRAD) D[b] = fma(D[b], a[b], P[b]);
+            P[b] = fma(P[b], a[b], row[b][k]);
         }
     }
 }
@@ -138,6 +155,11 @@ __device__ void build_ratio_tables(const double* smat, double* R, int lag) {
 __device__ __forceinline__ int chunk_key(uint64_t v, int ch, int nch, int lag) {
     if (ch == nch - 1) return int(v & ((1u << (2 * (lag - CHUNK * ch))) - 1u));
     return int((v >> (2 * (lag - CHUNK * ch - CHUNK))) & 255u);
+}
+
+__device__ __forceinline__ int gchunk_key(uint64_t v, int ch, int nchg, int lag) {
+    if (ch == nchg - 1) return int(v & ((1u << (2 * (lag - GCHUNK * ch))) - 1u));
+    return int((v >> (2 * (lag - GCHUNK * ch - GCHUNK))) & uint32_t(GCOMBOS - 1));
 }
 
 __device__ __forceinline__ int symbol_at(uint64_t v, int j, int lag, int nstart) {
@@ -214,10 +236,10 @@ __device__ __forceinline__ bool linear_head_tile(const double* R, const double* 
 // differences.  Small counts: predicated rising factorials and one shared division; a lane with a
 // count above SMALLC redoes its row with the general routine (divergent, rare in sparse tables).
 template <bool GRAD>
-__device__ __forceinline__ void letters_term(const double (&conc)[A1], const Counts& r, uint32_t steps, double& add,
-                                             double& prod, double (&w)[A1]) {
+__device__ __forceinline__ void letters_term(const double* __restrict__ stir, const double (&conc)[A1], const Counts& r,
+                                             uint32_t steps, double& add, double& prod, double (&w)[A1]) {
     double P[A1], D[A1];
-    rf_letters<GRAD>(conc, r.c, steps, P, D);
+    rf_letters<GRAD>(stir, conc, r.c, steps, P, D);
     add = 0.0;
     if (GRAD) {
         double ri[A1];
@@ -257,14 +279,16 @@ __device__ __forceinline__ void total_term(double s, const Counts& r, double& ad
 }
 
 // sum_b c_b log p_b = add + log(prod)  (multiply_no_nan semantics, core.py:138-139)
-__device__ __forceinline__ void mn_term(const double (&p)[A1], const Counts& r, uint32_t steps, double& add, double& prod) {
+__device__ __forceinline__ void mn_term(const double (&p)[A1], const Counts& r, double& add, double& prod) {
     double pw[A1];
 #pragma unroll
-    for (int b = 0; b < A1; ++b) pw[b] = r.c[b] >= 1 ? p[b] : 1.0;
-    for (uint32_t t = 1; t < steps; ++t) {
-#pragma unroll
-        for (int b = 0; b < A1; ++b)
-            if (r.c[b] > t) pw[b] *= p[b];
+    for (int b = 0; b < A1; ++b) {           // p^c for c <= 8 by squaring
+        const double p2 = p[b] * p[b], p4 = p2 * p2;
+        const uint32_t c = r.c[b];
+        double x = (c & 1u) ? p[b] : 1.0;
+        x *= (c & 2u) ? p2 : 1.0;
+        x *= (c & 4u) ? p4 : 1.0;
+        pw[b] = (c & 8u) ? p4 * p4 : x;
     }
     add = 0.0;
     prod = ((pw[0] * pw[1]) * (pw[2] * pw[3])) * pw[4];
@@ -315,15 +339,16 @@ __device__ __forceinline__ int noisy_argmax5(const double (&v)[A1], double sigma
         return best;
     }
     double nb = -INFINITY;
-#pragma unroll
-    for (int b = 0; b < A1; ++b)
-        if (v[b] > thr) {
-            const double x = v[b] + sigma * rng_normal(uint64_t(seed), row, model * 64 + uint64_t(b));
+    for (int b = 0; b < A1; ++b) {
+        const double vb = b == 0 ? v[0] : b == 1 ? v[1] : b == 2 ? v[2] : b == 3 ? v[3] : v[4];
+        if (vb > thr) {
+            const double x = vb + sigma * rng_normal(uint64_t(seed), row, model * 64 + uint64_t(b));
             if (x > nb) {
                 nb = x;
                 best = b;
             }
         }
+    }
     return best;
 }
 
@@ -342,8 +367,9 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partials, int 
 // ------------------------------------------------------------------------------------------------
 // Per iteration a CTA handles NW tiles of 32 rows.  Phase A: every warp computes one tile (one row per
 // lane) and stages (k-mer payload, g_0..g_3) -- the gradient w.r.t. the logits -- in shared memory.
-// Phase B: warp ch < nch owns chunk table G[ch]; it walks the NW staged tiles, groups equal chunk keys
-// inside a tile with match.any, and the group leader does a plain read-modify-write.  No atomics.
+// Phase B: warp ch owns gradient chunk table G[ch] (4 positions, 256 keys); it walks the NW staged tiles;
+// rows of a tile that collide on a key are serialised through a tag array, the winner does a plain
+// read-modify-write.  No atomics.
 template <bool TRAIN_AR>
 __global__ void __launch_bounds__(THREADS, 2)
 linear_train_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ col, int64_t stride,
@@ -351,15 +377,21 @@ linear_train_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restri
                     double* __restrict__ ll_out, double* __restrict__ partials) {
     extern __shared__ __align__(16) double smem[];
     const int nch = num_chunks(lag);
+    const int nchg = num_gchunks(lag);
     double* R = smem;                              // [nch][256][4] forward ratio tables
-    double* G = R + nch * COMBOS * 4;              // [nch][256][4] d ll / d chunk-logits (letters 0..3)
-    double* smat = G + nch * COMBOS * 4;           // [lag][5][5]
+    double* G = R + nch * COMBOS * 4;              // [nchg][256][4] d ll / d chunk-logits (letters 0..3)
+    double* smat = G + nchg * GCOMBOS * 4;         // [lag][5][5]
     double* gmat = smat + lag * A1 * A1;           // [lag][5][5]  gradient from slow-path rows (rare)
     double* tab_lg = gmat + lag * A1 * A1;         // [TABN] lgamma(S0 + N) - lgamma(S0)
     double* tab_dg = tab_lg + TABN;                // [TABN] digamma difference
     double* red = tab_dg + TABN;                   // [32]
-    double* stage_g = red + 32;                    // [NW][4][32]
+    double* stir = red + 32;                       // [(SMALLC+1)^2] Stirling triangle
+    double* stage_g = stir + STIR_N;               // [NW][4][32]
     uint64_t* stage_k = reinterpret_cast<uint64_t*>(stage_g + NW * 4 * 32);   // [NW][32]
+    uint64_t* slow_k = stage_k + NW * 32;                                      // [NW][SLOWCAP] start-padded rows
+    double* slow_g = reinterpret_cast<double*>(slow_k + NW * SLOWCAP);         // [NW][SLOWCAP][5]
+    int* slow_n = reinterpret_cast<int*>(slow_g + NW * SLOWCAP * A1);          // [NW]
+    uint8_t* tags = reinterpret_cast<uint8_t*>(slow_n + NW);                   // [nchg][256] scatter tie-break
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double hinv = exp(-h_signed[0]);         // 1 / h,  h = exp(h_signed)  (bear_net.py:186)
@@ -367,7 +399,8 @@ linear_train_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restri
         smat[i] = mat[i];
         gmat[i] = 0.0;
     }
-    for (int i = threadIdx.x; i < nch * COMBOS * 4; i += blockDim.x) G[i] = 0.0;
+    for (int i = threadIdx.x; i < nchg * GCOMBOS * 4; i += blockDim.x) G[i] = 0.0;
+    for (int i = threadIdx.x; i < STIR_N; i += blockDim.x) stir[i] = kStirling[i];
     if (!TRAIN_AR && threadIdx.x < TABN) {
         // the concentrations of a row sum to 1/h + 5 eps whatever its k-mer (softmax sums to 1)
         const LgDg t = lgdg_diff<true>(hinv + A1 * BEAR_EPS, double(threadIdx.x));
@@ -399,7 +432,7 @@ linear_train_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restri
                 double p[A1], ri[A1];
 #pragma unroll
                 for (int b = 0; b < A1; ++b) p[b] = f[b] + BEAR_EPS;                 // bear_net.py:68
-                mn_term(p, r, steps, add, prod);
+                mn_term(p, r, add, prod);
                 inv5(p, ri);
                 double u = 0.0;
 #pragma unroll
@@ -413,7 +446,7 @@ linear_train_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restri
                 double conc[A1];
 #pragma unroll
                 for (int b = 0; b < A1; ++b) conc[b] = fma(f[b], hinv, BEAR_EPS);       // bear_net.py:43
-                letters_term<true>(conc, r, steps, add, prod, w);
+                letters_term<true>(stir, conc, r, steps, add, prod, w);
                 double tadd, tdg;
                 if (r.n < double(TABN)) {
                     tadd = tab_lg[int(r.n)];
@@ -446,19 +479,32 @@ linear_train_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restri
         }
         if (ll_out && in_range) ll_out[i] = ll_row;
         const uint64_t key = (live && fast) ? (code & PAYLOAD_MASK) : KEY_INVALID;
-        // start-padded k-mers: the warp scatters them position by position (lane j = position j)
-        unsigned todo = __ballot_sync(0xffffffffu, live && !fast);
-        while (todo) {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const uint64_t cs = __shfl_sync(0xffffffffu, code, src);
-            double gs[A1];
+        // start-padded k-mers (rare): staged separately, up to SLOWCAP per tile; one warp owns the
+        // per-position table gmat in phase B.  Overflow rows are scattered right here with atomics,
+        // lane j handling position j.
+        const bool slow = live && !fast;
+        unsigned todo = __ballot_sync(0xffffffffu, slow);
+        if (lane == 0) slow_n[warp] = min(__popc(todo), SLOWCAP);
+        if (todo) {
+            const int rank = __popc(todo & ((1u << lane) - 1u));
+            if (slow && rank < SLOWCAP) {
+                slow_k[warp * SLOWCAP + rank] = code;
 #pragma unroll
-            for (int b = 0; b < A1; ++b) gs[b] = __shfl_sync(0xffffffffu, g[b], src);
-            if (lane < lag) {
-                double* dst = gmat + (lane * A1 + symbol_at(cs & PAYLOAD_MASK, lane, lag, int(cs >> 58))) * A1;
+                for (int b = 0; b < A1; ++b) slow_g[(warp * SLOWCAP + rank) * A1 + b] = g[b];
+            }
+            todo = __ballot_sync(0xffffffffu, slow && rank >= SLOWCAP);
+            while (todo) {
+                const int src = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const uint64_t cs = __shfl_sync(0xffffffffu, code, src);
+                double gs[A1];
 #pragma unroll
-                for (int b = 0; b < A1; ++b) atomicAdd(dst + b, gs[b]);
+                for (int b = 0; b < A1; ++b) gs[b] = __shfl_sync(0xffffffffu, g[b], src);
+                if (lane < lag) {
+                    double* dst = gmat + (lane * A1 + symbol_at(cs & PAYLOAD_MASK, lane, lag, int(cs >> 58))) * A1;
+#pragma unroll
+                    for (int b = 0; b < A1; ++b) atomicAdd(dst + b, gs[b]);
+                }
             }
         }
         stage_k[warp * 32 + lane] = key;
@@ -466,37 +512,48 @@ linear_train_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restri
         for (int b = 0; b < 4; ++b) stage_g[(warp * 4 + b) * 32 + lane] = g[b];
         __syncthreads();
         // ---------------- phase B: warp ch scatters chunk ch of every staged tile ----------------
-        if (warp < nch) {
-            const int ch = warp;
-            double* Gc = G + ch * COMBOS * 4;
+        // Rows of a tile with equal chunk keys collide on one table entry.  Each pending lane writes its
+        // id into tags[q]; whoever reads its own id back owns q this round and does a plain
+        // read-modify-write; the others retry (two rows of 32 rarely share one of 256 keys).
+        for (int ch = warp; ch < nchg; ch += NW) {
+            double* Gc = G + ch * GCOMBOS * 4;
+            uint8_t* tg = tags + ch * GCOMBOS;
             for (int t = 0; t < NW; ++t) {
                 const uint64_t k = stage_k[t * 32 + lane];
-                const bool valid = k != KEY_INVALID;
-                if (!__any_sync(0xffffffffu, valid)) continue;
-                const int q = valid ? chunk_key(k, ch, nch, lag) : 0x7fffffff;
-                const unsigned grp = __match_any_sync(0xffffffffu, q);
-                if (valid && (__ffs(grp) - 1) == lane) {
-                    const double* sg = stage_g + t * 4 * 32;
-                    double s0 = sg[lane], s1 = sg[32 + lane], s2 = sg[64 + lane], s3 = sg[96 + lane];
-                    unsigned rest = grp & (grp - 1);
-                    while (rest) {
-                        const int j = __ffs(rest) - 1;
-                        rest &= rest - 1;
-                        s0 += sg[j];
-                        s1 += sg[32 + j];
-                        s2 += sg[64 + j];
-                        s3 += sg[96 + j];
+                bool pending = k != KEY_INVALID;
+                if (!__any_sync(0xffffffffu, pending)) continue;
+                const int q = pending ? gchunk_key(k, ch, nchg, lag) : 0;
+                const double* sg = stage_g + t * 4 * 32;
+                const double s0 = sg[lane], s1 = sg[32 + lane], s2 = sg[64 + lane], s3 = sg[96 + lane];
+                do {
+                    if (pending) tg[q] = uint8_t(lane);
+                    __syncwarp();
+                    if (pending && tg[q] == uint8_t(lane)) {
+                        double2* dst = reinterpret_cast<double2*>(Gc + q * 4);
+                        double2 a = dst[0], b2 = dst[1];
+                        a.x += s0;
+                        a.y += s1;
+                        b2.x += s2;
+                        b2.y += s3;
+                        dst[0] = a;
+                        dst[1] = b2;
+                        pending = false;
                     }
-                    double2* dst = reinterpret_cast<double2*>(Gc + q * 4);
-                    double2 a = dst[0], b2 = dst[1];
-                    a.x += s0;
-                    a.y += s1;
-                    b2.x += s2;
-                    b2.y += s3;
-                    dst[0] = a;
-                    dst[1] = b2;
+                } while (__any_sync(0xffffffffu, pending));
+            }
+        }
+        if (warp == (nchg < NW ? nchg : 0)) {       // owner of gmat: the first warp without a chunk table
+            for (int t = 0; t < NW; ++t) {
+                const int cnt = slow_n[t];
+                for (int k = 0; k < cnt; ++k) {
+                    const uint64_t cs = slow_k[t * SLOWCAP + k];
+                    if (lane < lag) {
+                        double* dst = gmat + (lane * A1 + symbol_at(cs & PAYLOAD_MASK, lane, lag, int(cs >> 58))) * A1;
+                        const double* gs = slow_g + (t * SLOWCAP + k) * A1;
+#pragma unroll
+                        for (int b = 0; b < A1; ++b) dst[b] += gs[b];
+                    }
                 }
-                __syncwarp();
             }
         }
         __syncthreads();
@@ -517,13 +574,13 @@ linear_train_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restri
         const int b = idx % A1, s = (idx / A1) % A1, j = idx / (A1 * A1);
         double val = gmat[idx];
         if (s < 4) {
-            const int ch = j / CHUNK, p = j % CHUNK;
-            const int r = (ch == nch - 1) ? lag - CHUNK * ch : CHUNK;
+            const int ch = j / GCHUNK, p = j % GCHUNK;
+            const int r = (ch == nchg - 1) ? lag - GCHUNK * ch : GCHUNK;
             const int shift = 2 * (r - 1 - p);
             double acc = 0.0;
             for (int q = 0; q < (1 << (2 * r)); ++q) {
                 if (((q >> shift) & 3) != s) continue;
-                const double* src = G + (ch * COMBOS + q) * 4;
+                const double* src = G + (ch * GCOMBOS + q) * 4;
                 if (b < 4) acc += src[b];
                 else acc -= (src[0] + src[1]) + (src[2] + src[3]);   // the 5 logit gradients sum to 0
             }
@@ -542,6 +599,9 @@ explicit_train_kernel(const uint32_t* __restrict__ col, int64_t stride, int64_t 
                       const double* __restrict__ f_in, const double* __restrict__ h_signed, double scale,
                       double* __restrict__ gf, double* __restrict__ ll_out, double* __restrict__ partials) {
     __shared__ double red[32];
+    __shared__ double stir[STIR_N];
+    for (int i = threadIdx.x; i < STIR_N; i += blockDim.x) stir[i] = kStirling[i];
+    __syncthreads();
     const double hinv = exp(-h_signed[0]);
     double ll_sum = 0.0, dh_sum = 0.0;
     // warp-tile loop: every lane of a warp runs the same number of iterations (collectives inside)
@@ -562,14 +622,14 @@ explicit_train_kernel(const uint32_t* __restrict__ col, int64_t stride, int64_t 
             double p[A1];
 #pragma unroll
             for (int b = 0; b < A1; ++b) p[b] = f[b] + BEAR_EPS;
-            mn_term(p, r, steps, add, prod);
+            mn_term(p, r, add, prod);
 #pragma unroll
             for (int b = 0; b < A1; ++b) df[b] = r.c[b] == 0 ? 0.0 : double(r.c[b]) / p[b];
         } else {
             double conc[A1], tadd, tprod, tdg;
 #pragma unroll
             for (int b = 0; b < A1; ++b) conc[b] = fma(f[b], hinv, BEAR_EPS);
-            letters_term<true>(conc, r, steps, add, prod, w);
+            letters_term<true>(stir, conc, r, steps, add, prod, w);
             const double s = ((conc[0] + conc[1]) + (conc[2] + conc[3])) + conc[4];
             total_term<true>(s, r, tadd, tprod, tdg);
             add -= tadd;
@@ -605,7 +665,7 @@ explicit_train_kernel(const uint32_t* __restrict__ col, int64_t stride, int64_t 
 // ------------------------------------------------------------------------------------------------
 // NM bounds both the number of h values (H) and of BMM priors (V) of one launch.
 template <int HEAD, int NM, bool HAS_TRAIN>
-__global__ void __launch_bounds__(THREADS, 2)
+__global__ void __launch_bounds__(THREADS, NM <= 4 ? 3 : 2)
 eval_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ test_col,
             const uint32_t* __restrict__ train_col, int64_t stride, int64_t row0, int64_t n, int lag,
             const double* __restrict__ head, const double* __restrict__ d_h, int H,
@@ -622,6 +682,8 @@ eval_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ tes
     double* tab_ear = red + 32;                    // [NM][TABN]  lgamma(S0_k + N) - lgamma(S0_k)
     double* tab_van = tab_ear + NM * TABN;         // [NM][TABN]  lgamma(van_k + eps + c) - lgamma(van_k + eps)
     double* tab_vtot = tab_van + NM * TABN;        // [NM][TABN]  lgamma(5 (van_k + eps) + N) - lgamma(5 (van_k + eps))
+    double* stir = tab_vtot + NM * TABN;           // Stirling triangle
+    for (int i = threadIdx.x; i < STIR_N; i += blockDim.x) stir[i] = kStirling[i];
     if (LIN) {
         for (int i = threadIdx.x; i < lag * A1 * A1; i += blockDim.x) smat[i] = head[i];
         __syncthreads();
@@ -687,7 +749,7 @@ eval_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ tes
                 double conc[A1], add, prod;
 #pragma unroll
                 for (int b = 0; b < A1; ++b) conc[b] = fma(f[b], hinv[k], t[b]) + BEAR_EPS;
-                letters_term<false>(conc, r, steps, add, prod, dummy);
+                letters_term<false>(stir, conc, r, steps, add, prod, dummy);
                 if (TOT_TAB && use_tab) {
                     add -= tab_ear[k * TABN + int(r.n)];
                 } else {
@@ -709,7 +771,7 @@ eval_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ tes
             double p[A1], add, prod;
 #pragma unroll
             for (int b = 0; b < A1; ++b) p[b] = f[b] + BEAR_EPS;
-            mn_term(p, r, steps, add, prod);
+            mn_term(p, r, add, prod);
             if (live) {
                 arm_add += add;
                 arm_prod.push(0.0, prod);
@@ -737,7 +799,7 @@ eval_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ tes
                     }
                 } else {
                     double add, prod, tadd, tprod, tdg;
-                    letters_term<false>(conc, r, steps, add, prod, dummy);
+                    letters_term<false>(stir, conc, r, steps, add, prod, dummy);
                     const double s = ((conc[0] + conc[1]) + (conc[2] + conc[3])) + conc[4];
                     total_term<false>(s, r, tadd, tprod, tdg);
                     if (live) van_add[k] += (add - tadd) + log(prod / tprod);
@@ -847,12 +909,14 @@ int grid_for(int64_t n, int cap = MAX_GRID) {
 }
 
 size_t train_smem_bytes(int lag) {
-    return sizeof(double) * (size_t(num_chunks(lag)) * COMBOS * 4 * 2 + size_t(lag) * A1 * A1 * 2 + 2 * TABN + 32 +
-                             NW * 4 * 32 + NW * 32);
+    return sizeof(double) * (size_t(num_chunks(lag)) * COMBOS * 4 + size_t(num_gchunks(lag)) * GCOMBOS * 4 +
+                             size_t(lag) * A1 * A1 * 2 + 2 * TABN + 32 + STIR_N + NW * 4 * 32 + NW * 32 +
+                             NW * SLOWCAP * (1 + A1)) +
+           sizeof(int) * NW + size_t(num_gchunks(lag)) * GCOMBOS;
 }
 
 size_t eval_smem_bytes(int head, int lag, int nm) {
-    size_t d = 32 + size_t(3) * nm * TABN;
+    size_t d = 32 + size_t(3) * nm * TABN + STIR_N;
     if (head == BEAR_HEAD_LINEAR) d += size_t(num_chunks(lag)) * COMBOS * 4 + size_t(lag) * A1 * A1;
     return sizeof(double) * d;
 }
@@ -964,8 +1028,8 @@ extern "C" int bear_eval_step(const uint64_t* d_kmers, const uint32_t* d_test_co
     if (head == BEAR_HEAD_EXPLICIT) BEAR_REQUIRE(d_head != nullptr, fn);
     if (n == 0) return BEAR_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int grid = grid_for(n, 148 * 2);
     const int nm = H > V ? H : V;
+    const int grid = grid_for(n, 148 * (nm <= 4 ? 3 : 2));
     const int nmt = nm <= 1 ? 1 : nm <= 4 ? 4 : 8;
     const size_t smem = eval_smem_bytes(head, lag, nmt);
     const uint64_t* km = d_kmers ? d_kmers + row0 : nullptr;
