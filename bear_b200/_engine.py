@@ -45,8 +45,8 @@ class FlatParams:
     the user (and captured by plugin closures) are re-pointed to views of it, so the optimizer
     kernel and the allreduce see a single buffer while ``ar_func`` keeps working unchanged."""
 
-    def __init__(self, tensors):
-        dev = _lib.device()
+    def __init__(self, tensors, device=None):
+        dev = _lib.device() if device is None else torch.device(device)
         self.tensors = list(tensors)
         self.sizes = [int(t.numel()) for t in self.tensors]
         self.total = sum(self.sizes)

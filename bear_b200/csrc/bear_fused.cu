@@ -309,6 +309,39 @@ __device__ __forceinline__ double pick5(const uint32_t (&c)[A1], int idx) {
 // the maximum (anything further cannot win, P < 1e-28).  One candidate: no randomness needed.  All
 // candidates exactly tied: a uniform pick, which is what iid noise gives.  Otherwise Gaussian noise on
 // the candidates only.  seed < 0: no noise, first maximum wins.
+struct V5 {
+    double v[A1];
+};
+
+__device__ __forceinline__ uint32_t tie_hash(int64_t seed, uint64_t row, uint64_t model) {
+    return uint32_t(mix64(uint64_t(seed) ^ (row * 0x9E3779B97F4A7C15ull) ^ (model * 0xD1B54A32D192ED03ull)) >> 32);
+}
+
+// the randomised part, out of line: ties are rare except for the unconditioned BMM (handled separately)
+__device__ __noinline__ int argmax_tiebreak(V5 x, double top, double thr, bool all_exact, int exact, double sigma,
+                                            int64_t seed, uint64_t row, uint64_t model) {
+    int best = 0;
+    if (all_exact) {
+        int k = int(tie_hash(seed, row, model) % uint32_t(exact));
+        for (int b = 0; b < A1; ++b)
+            if (x.v[b] == top) {
+                if (k == 0) best = b;
+                --k;
+            }
+        return best;
+    }
+    double nb = -INFINITY;
+    for (int b = 0; b < A1; ++b)
+        if (x.v[b] > thr) {
+            const double y = x.v[b] + sigma * rng_normal(uint64_t(seed), row, model * 64 + uint64_t(b));
+            if (y > nb) {
+                nb = y;
+                best = b;
+            }
+        }
+    return best;
+}
+
 __device__ __forceinline__ int noisy_argmax5(const double (&v)[A1], double sigma, int64_t seed, uint64_t row,
                                              uint64_t model) {
     int best = 0;
@@ -328,28 +361,10 @@ __device__ __forceinline__ int noisy_argmax5(const double (&v)[A1], double sigma
         exact += v[b] == top;
     }
     if (near == 1) return best;
-    if (near == exact) {
-        int k = int(rng_u64(uint64_t(seed), row, model * 64 + 63) % uint64_t(exact));
+    V5 x;
 #pragma unroll
-        for (int b = 0; b < A1; ++b)
-            if (v[b] == top) {
-                if (k == 0) best = b;
-                --k;
-            }
-        return best;
-    }
-    double nb = -INFINITY;
-    for (int b = 0; b < A1; ++b) {
-        const double vb = b == 0 ? v[0] : b == 1 ? v[1] : b == 2 ? v[2] : b == 3 ? v[3] : v[4];
-        if (vb > thr) {
-            const double x = vb + sigma * rng_normal(uint64_t(seed), row, model * 64 + uint64_t(b));
-            if (x > nb) {
-                nb = x;
-                best = b;
-            }
-        }
-    }
-    return best;
+    for (int b = 0; b < A1; ++b) x.v[b] = v[b];
+    return argmax_tiebreak(x, top, thr, near == exact, exact, sigma, seed, row, model);
 }
 
 // Fixed-order second stage: out[p] += mult * sum_blk partials[blk, p]
@@ -804,7 +819,11 @@ eval_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ tes
                     total_term<false>(s, r, tadd, tprod, tdg);
                     if (live) van_add[k] += (add - tadd) + log(prod / tprod);
                 }
-                if (live) cor_van[k] += pick5(r.c, noisy_argmax5(conc, 100.0 * BEAR_EPS, seed, grow, 200 + uint64_t(k)));
+                if (live) {
+                    const int best = HAS_TRAIN ? noisy_argmax5(conc, 100.0 * BEAR_EPS, seed, grow, 200 + uint64_t(k))
+                                               : (seed < 0 ? 0 : int(tie_hash(seed, grow, 200 + uint64_t(k)) % uint32_t(A1)));
+                    cor_van[k] += pick5(r.c, best);
+                }
             }
         }
     }

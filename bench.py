@@ -28,6 +28,9 @@ sys.path.insert(0, ROOT)
 LAG = 20
 TRAIN_BYTES_PER_ROW = 28          # 8 B packed k-mer + 5 x 4 B counts (one column)  SURVEY.md 8(d)
 EVAL_BYTES_PER_ROW = 28           # ds_loc_train = -1: k-mer + the test column
+# dram__bytes_read.sum + dram__bytes_write.sum of linear_train_kernel per row, from the ncu --set full capture
+# profiles/r1_final_train_raw.csv (7.519 GB + 0.008 GB over 268 435 456 rows)
+TRAIN_DRAM_BYTES_PER_ROW_NCU = 28.04
 DEFAULT_ROWS = 1 << 31
 
 
@@ -304,7 +307,9 @@ def run_ours(args, rank, world_size, local_rank):
                 'd2h_bytes_per_step': d2h, 'rows_per_gpu_per_step': e_rows},
         'gpu_launches': args.steps * 6,
         'roofline': {'bound': 'hbm', 'kernel': 'linear_train_kernel<false>', 'achieved': achieved, 'peak': peak,
-                     'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+                     'unit': 'GB/s', 'frac': achieved / peak, 'traffic': TRAIN_DRAM_BYTES_PER_ROW_NCU * n,
+                     'traffic_note': 'bytes per launch = ncu dram read+write per row (profiles/r1_final_train_raw.csv) x rows',
+                     'algorithmic_bytes': TRAIN_BYTES_PER_ROW * n,
                      'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s',
                      'kernel_ms': train_ms, 'bytes_per_row': TRAIN_BYTES_PER_ROW},
         'train_rows_per_s': n * world_size / (train_ms * 1e-3),
