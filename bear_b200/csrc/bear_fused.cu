@@ -27,10 +27,8 @@ namespace {
 using namespace bear;
 
 constexpr int A1 = 5;            // DNA/RNA letters + stop
-constexpr int CHUNK = 4;         // positions per forward chunk table (ratio tables R)
+constexpr int CHUNK = 4;         // at most 4 positions per chunk table (forward ratios R, gradient G)
 constexpr int COMBOS = 256;      // 4^CHUNK
-constexpr int GCHUNK = 4;        // positions per gradient chunk table (G)
-constexpr int GCOMBOS = 256;     // 4^GCHUNK
 constexpr int THREADS = 256;
 constexpr int NW = THREADS / 32;
 constexpr int MAX_GRID = 148 * 4;
@@ -40,7 +38,19 @@ constexpr uint64_t KEY_INVALID = ~0ull;
 constexpr int SLOWCAP = 8;       // start-padded rows per tile that are staged (more fall back to atomics)
 
 __host__ __device__ inline int num_chunks(int lag) { return (lag + CHUNK - 1) / CHUNK; }
-__host__ __device__ inline int num_gchunks(int lag) { return (lag + GCHUNK - 1) / GCHUNK; }
+
+// The lag positions are spread as evenly as possible over the chunks (13 = 4+3+3+3, not 4+4+4+1):
+// a chunk with very few keys would make every row of a tile collide in the gradient scatter.
+struct ChunkGeom {
+    int start, size;
+};
+__host__ __device__ inline ChunkGeom chunk_geom(int lag, int nch, int ch) {
+    const int base = lag / nch, extra = lag % nch;
+    ChunkGeom g;
+    g.size = base + (ch < extra ? 1 : 0);
+    g.start = ch * base + (ch < extra ? ch : extra);
+    return g;
+}
 
 // ------------------------------------------------------------------------------------------------
 // per-row pieces
@@ -59,7 +69,10 @@ __device__ __forceinline__ Counts load_counts(const uint32_t* __restrict__ col, 
 #pragma unroll
     for (int b = 0; b < A1; ++b) r.c[b] = in_range ? __ldg(col + b * stride + i) : 0u;
     r.cmax = max(max(max(r.c[0], r.c[1]), max(r.c[2], r.c[3])), r.c[4]);
-    r.n = (double(r.c[0]) + double(r.c[1])) + (double(r.c[2]) + double(r.c[3])) + double(r.c[4]);
+    if (r.cmax < (1u << 29))                   // the common case: one integer sum, one conversion
+        r.n = double((r.c[0] + r.c[1]) + (r.c[2] + r.c[3]) + r.c[4]);
+    else
+        r.n = (double(r.c[0]) + double(r.c[1])) + (double(r.c[2]) + double(r.c[3])) + double(r.c[4]);
     return r;
 }
 
@@ -137,12 +150,13 @@ __device__ void build_ratio_tables(const double* smat, double* R, int lag) {
     const int nch = num_chunks(lag);
     for (int idx = threadIdx.x; idx < nch * COMBOS; idx += blockDim.x) {
         const int ch = idx >> 8, q = idx & 255;
-        const int r = (ch == nch - 1) ? lag - CHUNK * ch : CHUNK;
+        const ChunkGeom cg = chunk_geom(lag, nch, ch);
+        const int r = cg.size;
         double l[A1] = {0, 0, 0, 0, 0};
         if (q < (1 << (2 * r))) {
             for (int p = 0; p < r; ++p) {
                 const int s = (q >> (2 * (r - 1 - p))) & 3;
-                const double* row = smat + ((CHUNK * ch + p) * A1 + s) * A1;
+                const double* row = smat + ((cg.start + p) * A1 + s) * A1;
 #pragma unroll
                 for (int b = 0; b < A1; ++b) l[b] += row[b];
             }
@@ -153,13 +167,8 @@ __device__ void build_ratio_tables(const double* smat, double* R, int lag) {
 }
 
 __device__ __forceinline__ int chunk_key(uint64_t v, int ch, int nch, int lag) {
-    if (ch == nch - 1) return int(v & ((1u << (2 * (lag - CHUNK * ch))) - 1u));
-    return int((v >> (2 * (lag - CHUNK * ch - CHUNK))) & 255u);
-}
-
-__device__ __forceinline__ int gchunk_key(uint64_t v, int ch, int nchg, int lag) {
-    if (ch == nchg - 1) return int(v & ((1u << (2 * (lag - GCHUNK * ch))) - 1u));
-    return int((v >> (2 * (lag - GCHUNK * ch - GCHUNK))) & uint32_t(GCOMBOS - 1));
+    const ChunkGeom cg = chunk_geom(lag, nch, ch);
+    return int((v >> (2 * (lag - cg.start - cg.size))) & ((1u << (2 * cg.size)) - 1u));
 }
 
 __device__ __forceinline__ int symbol_at(uint64_t v, int j, int lag, int nstart) {
@@ -392,10 +401,10 @@ linear_train_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restri
                     double* __restrict__ ll_out, double* __restrict__ partials) {
     extern __shared__ __align__(16) double smem[];
     const int nch = num_chunks(lag);
-    const int nchg = num_gchunks(lag);
+    const int nchg = nch;
     double* R = smem;                              // [nch][256][4] forward ratio tables
     double* G = R + nch * COMBOS * 4;              // [nchg][256][4] d ll / d chunk-logits (letters 0..3)
-    double* smat = G + nchg * GCOMBOS * 4;         // [lag][5][5]
+    double* smat = G + nchg * COMBOS * 4;         // [lag][5][5]
     double* gmat = smat + lag * A1 * A1;           // [lag][5][5]  gradient from slow-path rows (rare)
     double* tab_lg = gmat + lag * A1 * A1;         // [TABN] lgamma(S0 + N) - lgamma(S0)
     double* tab_dg = tab_lg + TABN;                // [TABN] digamma difference
@@ -414,7 +423,7 @@ linear_train_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restri
         smat[i] = mat[i];
         gmat[i] = 0.0;
     }
-    for (int i = threadIdx.x; i < nchg * GCOMBOS * 4; i += blockDim.x) G[i] = 0.0;
+    for (int i = threadIdx.x; i < nchg * COMBOS * 4; i += blockDim.x) G[i] = 0.0;
     for (int i = threadIdx.x; i < STIR_N; i += blockDim.x) stir[i] = kStirling[i];
     if (!TRAIN_AR && threadIdx.x < TABN) {
         // the concentrations of a row sum to 1/h + 5 eps whatever its k-mer (softmax sums to 1)
@@ -531,15 +540,41 @@ linear_train_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restri
         // id into tags[q]; whoever reads its own id back owns q this round and does a plain
         // read-modify-write; the others retry (two rows of 32 rarely share one of 256 keys).
         for (int ch = warp; ch < nchg; ch += NW) {
-            double* Gc = G + ch * GCOMBOS * 4;
-            uint8_t* tg = tags + ch * GCOMBOS;
+            double* Gc = G + ch * COMBOS * 4;
+            uint8_t* tg = tags + ch * COMBOS;
+            const bool small_keys = chunk_geom(lag, nchg, ch).size < CHUNK;
             for (int t = 0; t < NW; ++t) {
                 const uint64_t k = stage_k[t * 32 + lane];
                 bool pending = k != KEY_INVALID;
                 if (!__any_sync(0xffffffffu, pending)) continue;
-                const int q = pending ? gchunk_key(k, ch, nchg, lag) : 0;
+                const int q = pending ? chunk_key(k, ch, nchg, lag) : 0;
                 const double* sg = stage_g + t * 4 * 32;
-                const double s0 = sg[lane], s1 = sg[32 + lane], s2 = sg[64 + lane], s3 = sg[96 + lane];
+                double s0 = sg[lane], s1 = sg[32 + lane], s2 = sg[64 + lane], s3 = sg[96 + lane];
+                if (small_keys) {
+                    // few keys (chunk of < 4 positions): most rows collide, so combine equal keys first
+                    const unsigned grp = __match_any_sync(0xffffffffu, pending ? q : 0x7fffffff);
+                    if (pending && (__ffs(grp) - 1) == lane) {
+                        unsigned rest = grp & (grp - 1);
+                        while (rest) {
+                            const int j = __ffs(rest) - 1;
+                            rest &= rest - 1;
+                            s0 += sg[j];
+                            s1 += sg[32 + j];
+                            s2 += sg[64 + j];
+                            s3 += sg[96 + j];
+                        }
+                        double2* dst = reinterpret_cast<double2*>(Gc + q * 4);
+                        double2 a = dst[0], b2 = dst[1];
+                        a.x += s0;
+                        a.y += s1;
+                        b2.x += s2;
+                        b2.y += s3;
+                        dst[0] = a;
+                        dst[1] = b2;
+                    }
+                    __syncwarp();
+                    continue;
+                }
                 do {
                     if (pending) tg[q] = uint8_t(lane);
                     __syncwarp();
@@ -589,13 +624,15 @@ linear_train_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restri
         const int b = idx % A1, s = (idx / A1) % A1, j = idx / (A1 * A1);
         double val = gmat[idx];
         if (s < 4) {
-            const int ch = j / GCHUNK, p = j % GCHUNK;
-            const int r = (ch == nchg - 1) ? lag - GCHUNK * ch : GCHUNK;
+            int ch = 0;
+            ChunkGeom cg = chunk_geom(lag, nchg, 0);
+            while (j >= cg.start + cg.size) cg = chunk_geom(lag, nchg, ++ch);
+            const int p = j - cg.start, r = cg.size;
             const int shift = 2 * (r - 1 - p);
             double acc = 0.0;
             for (int q = 0; q < (1 << (2 * r)); ++q) {
                 if (((q >> shift) & 3) != s) continue;
-                const double* src = G + (ch * GCOMBOS + q) * 4;
+                const double* src = G + (ch * COMBOS + q) * 4;
                 if (b < 4) acc += src[b];
                 else acc -= (src[0] + src[1]) + (src[2] + src[3]);   // the 5 logit gradients sum to 0
             }
@@ -861,22 +898,22 @@ eval_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ tes
 // ------------------------------------------------------------------------------------------------
 // BMM marginal likelihood, every group and alpha
 // ------------------------------------------------------------------------------------------------
-template <int NA1>
-__global__ void __launch_bounds__(THREADS)
+template <int NA1, int NV>
+__global__ void __launch_bounds__(THREADS, NA1 == 5 ? 4 : 1)
 bmm_kernel(const uint32_t* __restrict__ counts, int64_t stride, int64_t n, int G,
            const double* __restrict__ d_alpha, int V, double* __restrict__ partials) {
     __shared__ double red[32];
-    __shared__ double tab[BEAR_MAX_MODELS][TABN];      // lgamma(a + c) - lgamma(a)
-    __shared__ double tab_tot[BEAR_MAX_MODELS][TABN];  // lgamma(A1 a + N) - lgamma(A1 a)
+    __shared__ double tab[NV][TABN];      // lgamma(a + c) - lgamma(a)
+    __shared__ double tab_tot[NV][TABN];  // lgamma(A1 a + N) - lgamma(A1 a)
     const int g = blockIdx.y;
     const uint32_t* col = counts + int64_t(g) * NA1 * stride;
-    double alpha[BEAR_MAX_MODELS], acc[BEAR_MAX_MODELS];
+    double alpha[NV], acc[NV];
 #pragma unroll
-    for (int k = 0; k < BEAR_MAX_MODELS; ++k) {
+    for (int k = 0; k < NV; ++k) {
         alpha[k] = k < V ? d_alpha[k] : 1.0;
         acc[k] = 0.0;
     }
-    for (int idx = threadIdx.x; idx < BEAR_MAX_MODELS * TABN; idx += blockDim.x) {
+    for (int idx = threadIdx.x; idx < NV * TABN; idx += blockDim.x) {
         const int k = idx / TABN;
         const double a = k < V ? d_alpha[k] : 1.0, c = double(idx % TABN);
         LgDg t = lgdg_diff<false>(a, c);
@@ -885,27 +922,28 @@ bmm_kernel(const uint32_t* __restrict__ counts, int64_t stride, int64_t n, int G
         tab_tot[k][idx % TABN] = t.add + (t.mul == 1.0 ? 0.0 : log(t.mul));
     }
     __syncthreads();
-    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
-        uint32_t c[NA1], cmax = 0;
-        double tot = 0.0;
+    auto row_term = [&](const uint32_t (&c)[NA1]) {
+        uint32_t cmax = 0, toti = 0;
 #pragma unroll
         for (int b = 0; b < NA1; ++b) {
-            c[b] = __ldg(col + b * stride + i);
             cmax = max(cmax, c[b]);
-            tot += double(c[b]);
+            toti += c[b] < uint32_t(TABN) ? c[b] : uint32_t(TABN);
         }
-        if (cmax == 0) continue;
-        if (tot < double(TABN)) {
+        if (cmax == 0) return;
+        if (toti < uint32_t(TABN)) {
 #pragma unroll
-            for (int k = 0; k < BEAR_MAX_MODELS; ++k) {
+            for (int k = 0; k < NV; ++k) {
                 if (k < V) {
                     double s = 0.0;
 #pragma unroll
                     for (int b = 0; b < NA1; ++b) s += tab[k][c[b]];
-                    acc[k] += s - tab_tot[k][int(tot)];
+                    acc[k] += s - tab_tot[k][toti];
                 }
             }
         } else {
+            double tot = 0.0;
+#pragma unroll
+            for (int b = 0; b < NA1; ++b) tot += double(c[b]);
             for (int k = 0; k < V; ++k) {
                 LogProd num, den;
                 den.push(lgdg_diff<false>(double(NA1) * alpha[k], tot));
@@ -914,6 +952,33 @@ bmm_kernel(const uint32_t* __restrict__ counts, int64_t stride, int64_t n, int G
                 acc[k] += logprod_diff(num, den);
             }
         }
+    };
+    // four rows per thread with 128-bit loads when the column is 16-byte aligned (row0 % 4 == 0)
+    const bool vec = (reinterpret_cast<uintptr_t>(col) & 15) == 0 && (stride & 3) == 0;
+    const int64_t nq = vec ? n / 4 : 0;
+    for (int64_t qd = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; qd < nq; qd += int64_t(gridDim.x) * blockDim.x) {
+        uint4 v[NA1];
+#pragma unroll
+        for (int b = 0; b < NA1; ++b) v[b] = __ldg(reinterpret_cast<const uint4*>(col + b * stride) + qd);
+        uint32_t c[NA1];
+#pragma unroll
+        for (int b = 0; b < NA1; ++b) c[b] = v[b].x;
+        row_term(c);
+#pragma unroll
+        for (int b = 0; b < NA1; ++b) c[b] = v[b].y;
+        row_term(c);
+#pragma unroll
+        for (int b = 0; b < NA1; ++b) c[b] = v[b].z;
+        row_term(c);
+#pragma unroll
+        for (int b = 0; b < NA1; ++b) c[b] = v[b].w;
+        row_term(c);
+    }
+    for (int64_t i = nq * 4 + int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+        uint32_t c[NA1];
+#pragma unroll
+        for (int b = 0; b < NA1; ++b) c[b] = __ldg(col + b * stride + i);
+        row_term(c);
     }
     for (int k = 0; k < V; ++k) {
         const double s = block_sum(acc[k], red);
@@ -928,10 +993,10 @@ int grid_for(int64_t n, int cap = MAX_GRID) {
 }
 
 size_t train_smem_bytes(int lag) {
-    return sizeof(double) * (size_t(num_chunks(lag)) * COMBOS * 4 + size_t(num_gchunks(lag)) * GCOMBOS * 4 +
+    return sizeof(double) * (size_t(num_chunks(lag)) * COMBOS * 4 + size_t(num_chunks(lag)) * COMBOS * 4 +
                              size_t(lag) * A1 * A1 * 2 + 2 * TABN + 32 + STIR_N + NW * 4 * 32 + NW * 32 +
                              NW * SLOWCAP * (1 + A1)) +
-           sizeof(int) * NW + size_t(num_gchunks(lag)) * GCOMBOS;
+           sizeof(int) * NW + size_t(num_chunks(lag)) * COMBOS;
 }
 
 size_t eval_smem_bytes(int head, int lag, int nm) {
@@ -1081,10 +1146,12 @@ extern "C" int bear_bmm_likelihood(const uint32_t* d_counts, int64_t stride, int
     if (n == 0) return BEAR_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const dim3 grid(grid_for(n), G);
-    if (A1v == 5)
-        bmm_kernel<5><<<grid, THREADS, 0, st>>>(d_counts + row0, stride, n, G, d_alpha, V, d_workspace);
+    if (A1v == 5 && V <= 4)
+        bmm_kernel<5, 4><<<grid, THREADS, 0, st>>>(d_counts + row0, stride, n, G, d_alpha, V, d_workspace);
+    else if (A1v == 5)
+        bmm_kernel<5, 8><<<grid, THREADS, 0, st>>>(d_counts + row0, stride, n, G, d_alpha, V, d_workspace);
     else
-        bmm_kernel<21><<<grid, THREADS, 0, st>>>(d_counts + row0, stride, n, G, d_alpha, V, d_workspace);
+        bmm_kernel<21, 8><<<grid, THREADS, 0, st>>>(d_counts + row0, stride, n, G, d_alpha, V, d_workspace);
     BEAR_LAUNCH_CHECK("bmm_kernel");
     reduce_partials_kernel<<<1, 64, 0, st>>>(d_workspace, int(grid.x), G * V, 1.0, d_out);
     BEAR_LAUNCH_CHECK("reduce_partials_kernel");

@@ -1,0 +1,98 @@
+"""Per-kernel throughput of the count-streaming kernels on synthetic tables (CUDA events, inputs >> L2).
+Prints one JSON object per kernel: rows/s, algorithmic GB/s and fraction of the measured HBM peak."""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from bear_b200 import _lib  # noqa: E402
+from bear_b200._lib import lib, check, ptr  # noqa: E402
+
+
+def timed(fn, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e-3
+
+
+def main():
+    dev = torch.device('cuda', 0)
+    torch.cuda.set_device(dev)
+    peak = 6650.0
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'])
+    except Exception:
+        pass
+    K = int(os.environ.get('ROWS', 1 << 28))
+    out = []
+
+    def report(name, secs, rows, bytes_per_row, note=''):
+        gbs = rows * bytes_per_row / secs / 1e9
+        out.append({'kernel': name, 'rows': rows, 'ms': secs * 1e3, 'rows_per_s': rows / secs, 'bytes_per_row': bytes_per_row,
+                    'achieved_gbs': gbs, 'frac_of_measured_hbm_peak': gbs / peak, 'note': note})
+        print(json.dumps(out[-1]), flush=True)
+
+    for lag, G, regime, tag in ((20, 1, 0, 'C5 sparse lag20 G1'), (13, 8, 0, 'C3 sparse lag13 G8'), (10, 2, 1, 'C2 dense lag10 G2')):
+        n = K // G if G > 1 else K
+        stride = (n + 3) // 4 * 4
+        kmers = torch.empty(stride, dtype=torch.int64, device=dev)
+        counts = torch.empty((G, 5, stride), dtype=torch.int32, device=dev)
+        check(lib.bear_synth_table(ptr(kmers), ptr(counts), stride, 0, n, lag, G, 20, regime, 10, _lib.stream()))
+        ws = torch.empty(lib.bear_workspace_doubles(n, lag, 0), dtype=torch.float64, device=dev)
+        alpha = torch.tensor([0.1, 1.0, 10.0], dtype=torch.float64, device=dev)
+        acc = torch.zeros(G * 3, dtype=torch.float64, device=dev)
+        t = timed(lambda: check(lib.bear_bmm_likelihood(ptr(counts), stride, 0, n, G, 5, ptr(alpha), 3, ptr(acc), ptr(ws), _lib.stream())))
+        report('bmm_kernel<5> V=3 [%s]' % tag, t, n, 20 * G)
+        mat = (torch.randn(lag, 5, 5, dtype=torch.float64, device=dev) * 0.05).contiguous()
+        hs = torch.zeros(1, dtype=torch.float64, device=dev)
+        flat = torch.zeros(2 + lag * 25, dtype=torch.float64, device=dev)
+        for ar in (0, 1):
+            t = timed(lambda: check(lib.bear_linear_train_step(ptr(kmers), ptr(counts), stride, 0, n, lag, ptr(mat), ptr(hs), 1.0, ar,
+                                                               ptr(flat), None, ptr(ws), _lib.stream())))
+            report('linear_train_kernel<%s> [%s]' % ('AR' if ar else 'BEAR', tag), t, n, 28)
+        h = torch.ones(1, dtype=torch.float64, device=dev)
+        eacc = torch.zeros(11, dtype=torch.float64, device=dev)
+        t = timed(lambda: check(lib.bear_eval_step(ptr(kmers), ptr(counts), None, stride, 0, n, lag, _lib.HEAD_LINEAR, ptr(mat), ptr(h), 1,
+                                                   ptr(alpha), 3, 7, ptr(eacc), ptr(ws), _lib.stream())))
+        report('eval_kernel<LINEAR> H=1 V=3 no-train [%s]' % tag, t, n, 28)
+        if G > 1:
+            tr = ctypes_off(counts, 5 * stride * 4)
+            t = timed(lambda: check(lib.bear_eval_step(ptr(kmers), tr, ptr(counts), stride, 0, n, lag, _lib.HEAD_LINEAR, ptr(mat), ptr(h), 1,
+                                                       ptr(alpha), 3, 7, ptr(eacc), ptr(ws), _lib.stream())))
+            report('eval_kernel<LINEAR> H=1 V=3 heldout [%s]' % tag, t, n, 48)
+        m = min(n, 1 << 24)
+        f = torch.full((m, 5), 0.2, dtype=torch.float64, device=dev)
+        gf = torch.empty_like(f)
+        t = timed(lambda: check(lib.bear_dm_train_step_explicit(ptr(counts), stride, 0, m, ptr(f), ptr(hs), 1.0, 0, ptr(flat), ptr(gf), None,
+                                                                ptr(ws), _lib.stream())))
+        report('explicit_train_kernel<BEAR> [%s]' % tag, t, m, 100, 'reads 20 B counts + 40 B f, writes 40 B df')
+        oh = torch.empty((m, lag, 5), dtype=torch.float64, device=dev)
+        t = timed(lambda: check(lib.bear_decode_onehot(ptr(kmers), m, lag, 0, ptr(oh), _lib.stream())))
+        report('decode_onehot_kernel [%s]' % tag, t, m, 8 + 40 * lag, 'writes the reference-shaped float64 one-hot')
+        dense = torch.empty((m, G, 5), dtype=torch.float64, device=dev)
+        t = timed(lambda: check(lib.bear_unpack_counts(ptr(counts), stride, 0, m, G, 5, ptr(dense), _lib.stream())))
+        report('unpack_counts_kernel [%s]' % tag, t, m, 60 * G)
+        del kmers, counts, oh, dense, f, gf
+        torch.cuda.empty_cache()
+    with open(os.path.join(ROOT, 'gpurun_out', 'kernel_bench.json'), 'w') as fh:
+        json.dump(out, fh, indent=1)
+
+
+def ctypes_off(t, nbytes):
+    import ctypes
+    return ctypes.c_void_p(t.data_ptr() + nbytes)
+
+
+if __name__ == '__main__':
+    os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+    main()
