@@ -257,14 +257,39 @@ def run_ours(args, rank, world_size, local_rank):
     dc = torch.empty_like(hc, device=dev)
     out_host = torch.empty(2 + P + acc.numel(), dtype=torch.float64).pin_memory()
 
+    copy_stream = torch.cuda.Stream(device=dev)
+    n_chunks = 8
+    bounds = [(e_rows * i // n_chunks) // 4 * 4 for i in range(n_chunks)] + [e_rows]
+    col_d = ctypes_ptr(dc)
+
     def e2e_step():
-        dk.copy_(hk, non_blocking=True)
-        dc.copy_(hc, non_blocking=True)
-        train_pass(dk, ctypes_ptr(dc), e_rows, e_stride)
-        eval_pass(dk, ctypes_ptr(dc), e_rows, e_stride)
+        # H2D in chunks on a copy stream; the training kernel of chunk i overlaps the copy of chunk i+1
+        # (the kernels accumulate into the flat buffer, so a batch may arrive in pieces).
+        main = torch.cuda.current_stream()
+        copy_stream.wait_stream(main)
+        events = []
+        with torch.cuda.stream(copy_stream):
+            for lo, hi in zip(bounds[:-1], bounds[1:]):
+                top = e_stride if hi == e_rows else hi
+                dk[lo:top].copy_(hk[lo:top], non_blocking=True)
+                for b in range(5):           # contiguous 1-D pieces: plain cudaMemcpyAsync each
+                    dc[0, b, lo:top].copy_(hc[0, b, lo:top], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+                events.append(ev)
+        grad.zero_()
+        for (lo, hi), ev in zip(zip(bounds[:-1], bounds[1:]), events):
+            main.wait_event(ev)
+            check(lib.bear_linear_train_step(ptr(dk), col_d, e_stride, lo, hi - lo, LAG, ptr(flat_params[1:]),
+                                             ptr(flat_params[:1]), scale, 0, ptr(grad), None, ptr(ws), _lib.stream()))
+        if world_size > 1:
+            dist.all_reduce(grad)
+        check(lib.bear_adam_update(ptr(flat_params), ptr(grad[1:]), ptr(m), ptr(v), 1 + P, 0.01, 0.9, 0.999, 1e-7,
+                                   ptr(step_ctr), _lib.stream()))
+        eval_pass(dk, col_d, e_rows, e_stride)
         out_host[:2 + P].copy_(grad, non_blocking=True)
         out_host[2 + P:].copy_(acc, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        main.synchronize()
 
     for _ in range(2):
         e2e_step()
