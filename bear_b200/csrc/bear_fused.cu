@@ -44,6 +44,9 @@ __host__ __device__ inline int num_chunks(int lag) { return (lag + CHUNK - 1) / 
 struct ChunkGeom {
     int start, size;
 };
+struct ChunkKeys {               // chunk sizes: base + 1 for the first `extra` chunks, base for the rest
+    int base, extra;
+};
 __host__ __device__ inline ChunkGeom chunk_geom(int lag, int nch, int ch) {
     const int base = lag / nch, extra = lag % nch;
     ChunkGeom g;
@@ -166,9 +169,13 @@ __device__ void build_ratio_tables(const double* smat, double* R, int lag) {
     }
 }
 
-__device__ __forceinline__ int chunk_key(uint64_t v, int ch, int nch, int lag) {
-    const ChunkGeom cg = chunk_geom(lag, nch, ch);
-    return int((v >> (2 * (lag - cg.start - cg.size))) & ((1u << (2 * cg.size)) - 1u));
+__device__ __forceinline__ int chunk_shift(int lag, int ch, const ChunkKeys& ck) {
+    const int size = ck.base + (ch < ck.extra ? 1 : 0);
+    const int start = ch * ck.base + (ch < ck.extra ? ch : ck.extra);
+    return 2 * (lag - start - size);
+}
+__device__ __forceinline__ uint32_t chunk_mask(int ch, const ChunkKeys& ck) {
+    return (1u << (2 * (ck.base + (ch < ck.extra ? 1 : 0)))) - 1u;
 }
 
 __device__ __forceinline__ int symbol_at(uint64_t v, int j, int lag, int nstart) {
@@ -177,10 +184,13 @@ __device__ __forceinline__ int symbol_at(uint64_t v, int j, int lag, int nstart)
 
 // softmax(sum_j mat[j, s_j, :]) of a start-free k-mer through the chunk tables; false if the ratio
 // product left the double range (the caller then takes the cooperative path)
-__device__ __forceinline__ bool linear_head_fast(const double* R, uint64_t v, int lag, int nch, double (&f)[A1]) {
+__device__ __forceinline__ bool linear_head_fast(const double* R, uint64_t v, int lag, const ChunkKeys& ck, int nch, double (&f)[A1]) {
     double p0 = 1.0, p1 = 1.0, p2 = 1.0, p3 = 1.0;
+    int sh = 2 * lag;                           // chunks run from the most significant symbols down
     for (int ch = 0; ch < nch; ++ch) {
-        const int q = chunk_key(v, ch, nch, lag);
+        const int bits = 2 * (ck.base + (ch < ck.extra ? 1 : 0));
+        sh -= bits;
+        const int q = int(uint32_t(v >> sh) & ((1u << bits) - 1u));
         const double2 a = *reinterpret_cast<const double2*>(R + (ch * COMBOS + q) * 4);
         const double2 b = *reinterpret_cast<const double2*>(R + (ch * COMBOS + q) * 4 + 2);
         p0 *= a.x;
@@ -204,12 +214,12 @@ __device__ __forceinline__ bool linear_head_fast(const double* R, uint64_t v, in
 // weight row of position j, and a butterfly sum gives every lane the logits.  Must be called by all 32
 // lanes.  Returns true for lanes that took the chunk-table path (their gradient can be staged by key).
 __device__ __forceinline__ bool linear_head_tile(const double* R, const double* smat, uint64_t code, bool live,
-                                                 int lag, int nch, double (&f)[A1]) {
+                                                 int lag, int nch, const ChunkKeys& ck, double (&f)[A1]) {
     const int lane = threadIdx.x & 31;
     bool fast = false;
 #pragma unroll
     for (int b = 0; b < A1; ++b) f[b] = 0.2;
-    if (live && (code >> 58) == 0) fast = linear_head_fast(R, code & PAYLOAD_MASK, lag, nch, f);
+    if (live && (code >> 58) == 0) fast = linear_head_fast(R, code & PAYLOAD_MASK, lag, ck, nch, f);
     unsigned todo = __ballot_sync(0xffffffffu, live && !fast);
     while (todo) {
         const int src = __ffs(todo) - 1;
@@ -397,8 +407,8 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partials, int 
 template <bool TRAIN_AR>
 __global__ void __launch_bounds__(THREADS, 2)
 linear_train_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ col, int64_t stride,
-                    int64_t n, int lag, const double* __restrict__ mat, const double* __restrict__ h_signed,
-                    double* __restrict__ ll_out, double* __restrict__ partials) {
+                    int64_t n, int lag, const ChunkKeys ck, const double* __restrict__ mat,
+                    const double* __restrict__ h_signed, double* __restrict__ ll_out, double* __restrict__ partials) {
     extern __shared__ __align__(16) double smem[];
     const int nch = num_chunks(lag);
     const int nchg = nch;
@@ -448,7 +458,7 @@ linear_train_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restri
         const bool live = r.cmax != 0;             // zero-count row: ll = 0 and every gradient is 0
         const uint32_t steps = warp_steps(live, r.cmax);
         double f[A1], g[A1] = {0, 0, 0, 0, 0};
-        const bool fast = linear_head_tile(R, smat, code, live, lag, nch, f);
+        const bool fast = linear_head_tile(R, smat, code, live, lag, nch, ck, f);
         double ll_row = 0.0;
         {
             double add, prod, w[A1];
@@ -542,12 +552,14 @@ linear_train_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restri
         for (int ch = warp; ch < nchg; ch += NW) {
             double* Gc = G + ch * COMBOS * 4;
             uint8_t* tg = tags + ch * COMBOS;
-            const bool small_keys = chunk_geom(lag, nchg, ch).size < CHUNK;
+            const uint32_t kmask = chunk_mask(ch, ck);
+            const bool small_keys = kmask < uint32_t(COMBOS - 1);
+            const int kshift = chunk_shift(lag, ch, ck);
             for (int t = 0; t < NW; ++t) {
                 const uint64_t k = stage_k[t * 32 + lane];
                 bool pending = k != KEY_INVALID;
                 if (!__any_sync(0xffffffffu, pending)) continue;
-                const int q = pending ? chunk_key(k, ch, nchg, lag) : 0;
+                const int q = pending ? int(uint32_t(k >> kshift) & kmask) : 0;
                 const double* sg = stage_g + t * 4 * 32;
                 double s0 = sg[lane], s1 = sg[32 + lane], s2 = sg[64 + lane], s3 = sg[96 + lane];
                 if (small_keys) {
@@ -715,12 +727,12 @@ explicit_train_kernel(const uint32_t* __restrict__ col, int64_t stride, int64_t 
 // ------------------------------------------------------------------------------------------------
 // evaluation
 // ------------------------------------------------------------------------------------------------
-// NM bounds both the number of h values (H) and of BMM priors (V) of one launch.
-template <int HEAD, int NM, bool HAS_TRAIN>
-__global__ void __launch_bounds__(THREADS, NM <= 4 ? 3 : 2)
+// NH / NV bound the number of h values (H) and of BMM priors (V) of one launch.
+template <int HEAD, int NH, int NV, bool HAS_TRAIN>
+__global__ void __launch_bounds__(THREADS, (NH <= 1 && NV <= 4) ? 3 : 2)
 eval_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ test_col,
             const uint32_t* __restrict__ train_col, int64_t stride, int64_t row0, int64_t n, int lag,
-            const double* __restrict__ head, const double* __restrict__ d_h, int H,
+            const ChunkKeys ck, const double* __restrict__ head, const double* __restrict__ d_h, int H,
             const double* __restrict__ d_van, int V, int64_t seed, double* __restrict__ partials) {
     extern __shared__ __align__(16) double smem[];
     const int nch = num_chunks(lag);
@@ -731,6 +743,7 @@ eval_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ tes
     double* R = smem;
     double* smat = R + (LIN ? nch * COMBOS * 4 : 0);
     double* red = smat + (LIN ? lag * A1 * A1 : 0);
+    constexpr int NM = NH > NV ? NH : NV;
     double* tab_ear = red + 32;                    // [NM][TABN]  lgamma(S0_k + N) - lgamma(S0_k)
     double* tab_van = tab_ear + NM * TABN;         // [NM][TABN]  lgamma(van_k + eps + c) - lgamma(van_k + eps)
     double* tab_vtot = tab_van + NM * TABN;        // [NM][TABN]  lgamma(5 (van_k + eps) + N) - lgamma(5 (van_k + eps))
@@ -741,12 +754,11 @@ eval_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ tes
         __syncthreads();
         build_ratio_tables(smat, R, lag);
     }
-    double hinv[NM], van[NM];
+    double hinv[NH], van[NV];
 #pragma unroll
-    for (int k = 0; k < NM; ++k) {
-        hinv[k] = k < H ? 1.0 / d_h[k] : 1.0;
-        van[k] = k < V ? d_van[k] : 1.0;
-    }
+    for (int k = 0; k < NH; ++k) hinv[k] = k < H ? 1.0 / d_h[k] : 1.0;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) van[k] = k < V ? d_van[k] : 1.0;
     if (!HAS_TRAIN) {
         for (int idx = threadIdx.x; idx < NM * TABN; idx += blockDim.x) {
             const int k = idx / TABN;
@@ -763,10 +775,12 @@ eval_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ tes
     }
     __syncthreads();
 
-    double ear_add[NM], cor_ear[NM], van_add[NM], cor_van[NM];
-    LogProd ear_prod[NM];
+    double ear_add[NH], cor_ear[NH], van_add[NV], cor_van[NV];
+    LogProd ear_prod[NH];
 #pragma unroll
-    for (int k = 0; k < NM; ++k) ear_add[k] = cor_ear[k] = van_add[k] = cor_van[k] = 0.0;
+    for (int k = 0; k < NH; ++k) ear_add[k] = cor_ear[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) van_add[k] = cor_van[k] = 0.0;
     double arm_add = 0.0, cor_arm = 0.0, total = 0.0;
     LogProd arm_prod;
 
@@ -783,7 +797,7 @@ eval_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ tes
         }
         double f[A1];
         if (LIN) {
-            linear_head_tile(R, smat, in_range ? __ldg(kmers + i) : 0ull, live, lag, nch, f);
+            linear_head_tile(R, smat, in_range ? __ldg(kmers + i) : 0ull, live, lag, nch, ck, f);
         } else {
 #pragma unroll
             for (int b = 0; b < A1; ++b)
@@ -796,7 +810,7 @@ eval_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ tes
         double dummy[A1];
         // BEAR: conc = f / h + train + eps   (bear_net.py:43, 335-337)
 #pragma unroll
-        for (int k = 0; k < NM; ++k) {
+        for (int k = 0; k < NH; ++k) {
             if (k < H) {
                 double conc[A1], add, prod;
 #pragma unroll
@@ -832,7 +846,7 @@ eval_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ tes
         }
         // vanilla BMM: conc = train + van + eps   (bear_net.py:328-331, 339-340)
 #pragma unroll
-        for (int k = 0; k < NM; ++k) {
+        for (int k = 0; k < NV; ++k) {
             if (k < V) {
                 double conc[A1];
 #pragma unroll
@@ -869,7 +883,7 @@ eval_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ tes
     double* out = partials + int64_t(blockIdx.x) * P;
     int o = 0;
 #pragma unroll
-    for (int k = 0; k < NM; ++k)
+    for (int k = 0; k < NH; ++k)
         if (k < H) {
             const double v = ear_add[k] + (ear_prod[k].add + (ear_prod[k].mul == 1.0 ? 0.0 : log(ear_prod[k].mul)));
             const double s = block_sum(v, red);
@@ -883,14 +897,14 @@ eval_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ tes
         ++o;
     }
 #pragma unroll
-    for (int k = 0; k < NM; ++k)
+    for (int k = 0; k < NV; ++k)
         if (k < V) { const double s = block_sum(van_add[k], red); if (threadIdx.x == 0) out[o] = s; ++o; }
 #pragma unroll
-    for (int k = 0; k < NM; ++k)
+    for (int k = 0; k < NH; ++k)
         if (k < H) { const double s = block_sum(cor_ear[k], red); if (threadIdx.x == 0) out[o] = s; ++o; }
     { const double s = block_sum(cor_arm, red); if (threadIdx.x == 0) out[o] = s; ++o; }
 #pragma unroll
-    for (int k = 0; k < NM; ++k)
+    for (int k = 0; k < NV; ++k)
         if (k < V) { const double s = block_sum(cor_van[k], red); if (threadIdx.x == 0) out[o] = s; ++o; }
     { const double s = block_sum(total, red); if (threadIdx.x == 0) out[o] = s; }
 }
@@ -986,6 +1000,14 @@ bmm_kernel(const uint32_t* __restrict__ counts, int64_t stride, int64_t n, int G
     }
 }
 
+ChunkKeys make_chunk_keys(int lag) {
+    ChunkKeys ck;
+    const int nch = num_chunks(lag);
+    ck.base = lag / nch;
+    ck.extra = lag % nch;
+    return ck;
+}
+
 int grid_for(int64_t n, int cap = MAX_GRID) {
     int64_t blocks = (n + THREADS - 1) / THREADS;
     if (blocks < 1) blocks = 1;
@@ -1013,31 +1035,32 @@ int set_smem(K kernel, size_t bytes) {
     return 0;
 }
 
-template <int HEAD, int NM, bool HAS_TRAIN>
+template <int HEAD, int NH, int NV, bool HAS_TRAIN>
 int launch_eval(int grid, size_t smem, cudaStream_t st, const uint64_t* km, const uint32_t* te, const uint32_t* tr,
                 int64_t stride, int64_t row0, int64_t n, int lag, const double* head, const double* d_h, int H,
                 const double* d_van, int V, int64_t seed, double* ws) {
-    if (set_smem(eval_kernel<HEAD, NM, HAS_TRAIN>, smem)) return BEAR_ERR_CUDA;
-    eval_kernel<HEAD, NM, HAS_TRAIN><<<grid, THREADS, smem, st>>>(km, te, tr, stride, row0, n, lag, head, d_h, H, d_van, V,
-                                                                  seed, ws);
+    if (set_smem(eval_kernel<HEAD, NH, NV, HAS_TRAIN>, smem)) return BEAR_ERR_CUDA;
+    eval_kernel<HEAD, NH, NV, HAS_TRAIN><<<grid, THREADS, smem, st>>>(km, te, tr, stride, row0, n, lag,
+                                                                      make_chunk_keys(lag > 0 && lag <= 29 ? lag : 1), head,
+                                                                      d_h, H, d_van, V, seed, ws);
     return 0;
 }
 
-template <int HEAD, int NM>
+template <int HEAD, int NH, int NV>
 int launch_eval_t(bool has_train, int grid, size_t smem, cudaStream_t st, const uint64_t* km, const uint32_t* te,
                   const uint32_t* tr, int64_t stride, int64_t row0, int64_t n, int lag, const double* head,
                   const double* d_h, int H, const double* d_van, int V, int64_t seed, double* ws) {
-    return has_train ? launch_eval<HEAD, NM, true>(grid, smem, st, km, te, tr, stride, row0, n, lag, head, d_h, H, d_van, V, seed, ws)
-                     : launch_eval<HEAD, NM, false>(grid, smem, st, km, te, tr, stride, row0, n, lag, head, d_h, H, d_van, V, seed, ws);
+    return has_train ? launch_eval<HEAD, NH, NV, true>(grid, smem, st, km, te, tr, stride, row0, n, lag, head, d_h, H, d_van, V, seed, ws)
+                     : launch_eval<HEAD, NH, NV, false>(grid, smem, st, km, te, tr, stride, row0, n, lag, head, d_h, H, d_van, V, seed, ws);
 }
 
+// the common call is one h value with up to four priors (evaluation); h_scan uses up to eight h values
 template <int HEAD>
-int launch_eval_nm(int nm, bool has_train, int grid, size_t smem, cudaStream_t st, const uint64_t* km, const uint32_t* te,
+int launch_eval_nm(bool small, bool has_train, int grid, size_t smem, cudaStream_t st, const uint64_t* km, const uint32_t* te,
                    const uint32_t* tr, int64_t stride, int64_t row0, int64_t n, int lag, const double* head,
                    const double* d_h, int H, const double* d_van, int V, int64_t seed, double* ws) {
-    if (nm <= 1) return launch_eval_t<HEAD, 1>(has_train, grid, smem, st, km, te, tr, stride, row0, n, lag, head, d_h, H, d_van, V, seed, ws);
-    if (nm <= 4) return launch_eval_t<HEAD, 4>(has_train, grid, smem, st, km, te, tr, stride, row0, n, lag, head, d_h, H, d_van, V, seed, ws);
-    return launch_eval_t<HEAD, 8>(has_train, grid, smem, st, km, te, tr, stride, row0, n, lag, head, d_h, H, d_van, V, seed, ws);
+    if (small) return launch_eval_t<HEAD, 1, 4>(has_train, grid, smem, st, km, te, tr, stride, row0, n, lag, head, d_h, H, d_van, V, seed, ws);
+    return launch_eval_t<HEAD, 8, 8>(has_train, grid, smem, st, km, te, tr, stride, row0, n, lag, head, d_h, H, d_van, V, seed, ws);
 }
 
 }  // namespace
@@ -1063,13 +1086,14 @@ extern "C" int bear_linear_train_step(const uint64_t* d_kmers, const uint32_t* d
     const int grid = grid_for(n, 148 * 2);
     const size_t smem = train_smem_bytes(lag);
     const int P = 2 + lag * A1 * A1;
+    const ChunkKeys ck = make_chunk_keys(lag);
     if (train_ar) {
         if (set_smem(linear_train_kernel<true>, smem)) return BEAR_ERR_CUDA;
-        linear_train_kernel<true><<<grid, THREADS, smem, st>>>(d_kmers + row0, d_col + row0, stride, n, lag, d_mat,
+        linear_train_kernel<true><<<grid, THREADS, smem, st>>>(d_kmers + row0, d_col + row0, stride, n, lag, ck, d_mat,
                                                               d_h_signed, d_ll_out, d_workspace);
     } else {
         if (set_smem(linear_train_kernel<false>, smem)) return BEAR_ERR_CUDA;
-        linear_train_kernel<false><<<grid, THREADS, smem, st>>>(d_kmers + row0, d_col + row0, stride, n, lag, d_mat,
+        linear_train_kernel<false><<<grid, THREADS, smem, st>>>(d_kmers + row0, d_col + row0, stride, n, lag, ck, d_mat,
                                                                d_h_signed, d_ll_out, d_workspace);
     }
     BEAR_LAUNCH_CHECK("linear_train_kernel");
@@ -1112,20 +1136,19 @@ extern "C" int bear_eval_step(const uint64_t* d_kmers, const uint32_t* d_test_co
     if (head == BEAR_HEAD_EXPLICIT) BEAR_REQUIRE(d_head != nullptr, fn);
     if (n == 0) return BEAR_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int nm = H > V ? H : V;
-    const int grid = grid_for(n, 148 * (nm <= 4 ? 3 : 2));
-    const int nmt = nm <= 1 ? 1 : nm <= 4 ? 4 : 8;
-    const size_t smem = eval_smem_bytes(head, lag, nmt);
+    const bool small = H <= 1 && V <= 4;
+    const int grid = grid_for(n, 148 * (small ? 3 : 2));
+    const size_t smem = eval_smem_bytes(head, lag, small ? 4 : 8);
     const uint64_t* km = d_kmers ? d_kmers + row0 : nullptr;
     const uint32_t* tr = d_train_col ? d_train_col + row0 : nullptr;
     const uint32_t* te = d_test_col + row0;
     const bool ht = tr != nullptr;
     int rc;
     switch (head) {
-        case BEAR_HEAD_LINEAR: rc = launch_eval_nm<BEAR_HEAD_LINEAR>(nm, ht, grid, smem, st, km, te, tr, stride, row0, n, lag, d_head, d_h, H, d_van, V, seed, d_workspace); break;
-        case BEAR_HEAD_EXPLICIT: rc = launch_eval_nm<BEAR_HEAD_EXPLICIT>(nm, ht, grid, smem, st, km, te, tr, stride, row0, n, lag, d_head, d_h, H, d_van, V, seed, d_workspace); break;
-        case BEAR_HEAD_STOP: rc = launch_eval_nm<BEAR_HEAD_STOP>(nm, ht, grid, smem, st, km, te, tr, stride, row0, n, lag, d_head, d_h, H, d_van, V, seed, d_workspace); break;
-        default: rc = launch_eval_nm<BEAR_HEAD_NONE>(nm, ht, grid, smem, st, km, te, tr, stride, row0, n, lag, d_head, d_h, H, d_van, V, seed, d_workspace); break;
+        case BEAR_HEAD_LINEAR: rc = launch_eval_nm<BEAR_HEAD_LINEAR>(small, ht, grid, smem, st, km, te, tr, stride, row0, n, lag, d_head, d_h, H, d_van, V, seed, d_workspace); break;
+        case BEAR_HEAD_EXPLICIT: rc = launch_eval_nm<BEAR_HEAD_EXPLICIT>(small, ht, grid, smem, st, km, te, tr, stride, row0, n, lag, d_head, d_h, H, d_van, V, seed, d_workspace); break;
+        case BEAR_HEAD_STOP: rc = launch_eval_nm<BEAR_HEAD_STOP>(small, ht, grid, smem, st, km, te, tr, stride, row0, n, lag, d_head, d_h, H, d_van, V, seed, d_workspace); break;
+        default: rc = launch_eval_nm<BEAR_HEAD_NONE>(small, ht, grid, smem, st, km, te, tr, stride, row0, n, lag, d_head, d_h, H, d_van, V, seed, d_workspace); break;
     }
     if (rc) return rc;
     BEAR_LAUNCH_CHECK("eval_kernel");
