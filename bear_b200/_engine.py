@@ -114,6 +114,14 @@ def onehot_rows(table, r0, n):
     return out
 
 
+def dense_counts(table, r0, n):
+    """The reference-shaped counts tensor [n, G, A1] (float64) of rows [r0, r0+n), on the device."""
+    k, c = table.device_tensors()
+    out = torch.empty((n, table.num_ds, table.A1), dtype=torch.float64, device=k.device)
+    check(lib.bear_unpack_counts(ptr(c), table.stride, r0, n, table.num_ds, table.A1, ptr(out), _lib.stream()))
+    return out
+
+
 def check_dataset(data):
     if not isinstance(data, KmerDataset):
         raise TypeError('data must be a KmerDataset from bear_b200.dataloader (dataloader / sparse_dataloader)')

@@ -124,7 +124,15 @@ def train(data, num_kmers, epochs, ds_loc, alphabet, lag, make_ar_func, af_kwarg
     ws = eng.workspace(table, fp.total)
     k, c = table.device_tensors()
 
-    if eng.fused_linear_ok(ar_func, table):
+    if table.A1 != 5:
+        # protein tables: dense route through the generic distribution kernels (any alphabet size)
+        def step_fn(r0, n, scale):
+            for c0 in range(r0, r0 + n, eng.EXPLICIT_CHUNK):
+                cn = min(eng.EXPLICIT_CHUNK, r0 + n - c0)
+                batch = (eng.onehot_rows(table, c0, cn), eng.dense_counts(table, c0, cn)[:, ds_loc, :])
+                grads = [fp.grad_view(i) for i in range(len(params))]
+                fp.grad[0] += _train_step(batch, scale * cn, h_signed, ar_func, params, grads, train_ar)
+    elif eng.fused_linear_ok(ar_func, table):
         mat = params[1]
 
         def step_fn(r0, n, scale):
@@ -197,6 +205,8 @@ def evaluation(data, ds_loc_train, ds_loc_test, alphabet, h, ar_func, van_reg, d
     accuracy_ear, accuracy_arm, accuracy_van) as float64 CPU tensors (``.numpy()`` works).
     """
     table = eng.check_dataset(data)
+    if table.A1 != 5:
+        return _dense_evaluation(data, ds_loc_train, ds_loc_test, h, ar_func, van_reg, seed)
     head, head_fn = _head_for_eval(ar_func, table)
     hv = float(h.item() if hasattr(h, 'item') else h)
     ll_ear, ll_arm, ll_van, ce, ca, cv, tot = eng.eval_loop(data, ds_loc_train, ds_loc_test, [hv], van_reg,
@@ -204,10 +214,33 @@ def evaluation(data, ds_loc_train, ds_loc_test, alphabet, h, ar_func, van_reg, d
     return eng.finish_evaluation(ll_ear[0], ll_arm, ll_van, ce[0], ca, cv, tot)
 
 
+def _dense_evaluation(data, ds_loc_train, ds_loc_test, h, ar_func, van_reg, seed):
+    """evaluation() for alphabets the fused kernels do not cover (protein): batches are unpacked on the
+    device and run through _evaluation_step (generic distribution kernels)."""
+    table = data.table
+    use_train = ds_loc_train >= 0
+    acc = None
+    for r0, n, _ in data.batches():
+        for c0 in range(r0, r0 + n, eng.EXPLICIT_CHUNK):
+            cn = min(eng.EXPLICIT_CHUNK, r0 + n - c0)
+            counts = eng.dense_counts(table, c0, cn)
+            batch = [eng.onehot_rows(table, c0, cn), counts[:, ds_loc_test, :]]
+            if use_train:
+                batch.append(counts[:, ds_loc_train, :])
+            with torch.no_grad():
+                out = _evaluation_step(batch, h, ar_func, van_reg, table.A1 - 1, use_train, seed=seed)
+            acc = list(out) if acc is None else [a + o for a, o in zip(acc, out)]
+    acc = [eng.allreduce_sum(a.reshape(-1)).cpu() for a in acc]
+    ll_ear, ll_arm, ll_van, ce, ca, cv, tot = acc
+    return eng.finish_evaluation(ll_ear[0], ll_arm[0], ll_van, ce[0], ca[0], cv, tot[0])
+
+
 def h_scan(data, ds_loc_train, ds_loc_test, alphabet, h, ar_func, dtype=torch.float64, seed=None):
     """Evaluate a trained BEAR model at several h values (bear_net.py:465-531).
     Returns (log_likelihood_ear[H], perplexity_ear[H], accuracy_ear[H])."""
     table = eng.check_dataset(data)
+    if table.A1 != 5:
+        raise NotImplementedError('h_scan covers the DNA / RNA alphabets; evaluate protein tables one h at a time')
     head, head_fn = _head_for_eval(ar_func, table)
     hv = np.asarray(h.cpu() if isinstance(h, torch.Tensor) else h, dtype=np.float64).reshape(-1)
     ll_ear, _, _, ce, _, _, tot = eng.eval_loop(data, ds_loc_train, ds_loc_test, hv, [1.0], head, head_fn, seed)

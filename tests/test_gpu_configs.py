@@ -129,3 +129,45 @@ def test_c4_cnn_lag13_four_groups_with_posterior_pass(cuda):
     assert np.max(np.abs(p.mean(-1) - mean)) < 6 * np.sqrt(var.max() / mc) + 1e-3
     big = var > 1e-4
     assert np.allclose(p.var(-1)[big], var[big], rtol=0.25)
+
+
+def test_protein_alphabet_dense_route(cuda):
+    """Protein tables (A+1 = 21, 5-bit packing, unknown residue 'X' -> zero one-hot row) train and evaluate
+    through the generic distribution kernels and match the oracle."""
+    from bear_b200 import ar_funcs, bear_net, dataloader as dl
+    from oracle import bear_oracle as O
+    rng = np.random.default_rng(3)
+    letters = O.ALPHABETS_IN['prot'][:-1]
+    K, lag = 400, 3
+    kmers = []
+    for i in range(K):
+        ns = int(rng.integers(0, lag + 1)) if rng.random() < 0.2 else 0
+        body = list(rng.choice(letters, size=lag - ns))
+        if body and rng.random() < 0.05:
+            body[-1] = 'X'
+        kmers.append('[' * ns + ''.join(body))
+    counts = rng.poisson(1.5, size=(K, 2, 21)) * (rng.random((K, 2, 21)) < 0.4)
+    table = dl.KmerTable.from_arrays(kmers, counts, 'prot')
+    assert [k.decode() for k in table.kmers_str()] == kmers
+    data = dl.KmerDataset(table, 150)
+    torch.manual_seed(12)
+    p0, _, _ = bear_net._create_params(lag, 20, ar_funcs.make_ar_func_linear, {})
+    p0 = [p.clone() for p in p0]
+    ls = []
+    params, h_signed, ar_func = bear_net.train(data, K, 1, 0, 'prot', lag, ar_funcs.make_ar_func_linear, {}, 0.01, 'Adam',
+                                               False, params_restart=p0, loss_save=ls)
+    oh, c = O.one_hot(kmers, 'prot'), torch.tensor(counts[:, 0].astype(np.float64))
+    batches = [(oh[i:i + 150], c[i:i + 150]) for i in range(0, K, 150)]
+    wl = []
+    wp, wh = O.train(batches, K, 'linear', [p0[1].cpu()], p0[0].cpu(), 0.01, False, loss_save=wl)
+    assert rel(ls, wl) <= 1e-10
+    assert rel(params[1].cpu().numpy(), wp[0].numpy()) <= 1e-8 and abs(float(h_signed) - float(wh)) <= 1e-9
+    h = float(torch.exp(h_signed))
+    got = bear_net.evaluation(data, 0, 1, 'prot', h, ar_func, [0.5, 2.0], seed=-1)
+    f = O.ar_linear(oh, [params[1].cpu()])
+    want = O.evaluation([(oh, f, counts[:, 1].astype(np.float64), counts[:, 0].astype(np.float64))],
+                        torch.tensor(h, dtype=torch.float64), np.array([0.5, 2.0]))
+    for g, w in zip(got, want):
+        assert rel(g.numpy(), w.numpy()) <= 1e-10
+    bm = dl.bmm_likelihood(data, [0.5, 2.0]).numpy()
+    assert rel(bm, O.bmm_likelihood(counts.astype(np.float64), np.array([0.5, 2.0])).numpy()) <= 1e-10
