@@ -223,6 +223,12 @@ __global__ void synth_table_kernel(uint64_t* __restrict__ kmers, uint32_t* __res
             code = (code * 0xD1B54A32D192ED03ull) & mask;
             code ^= code >> (bits / 3 + 1);
         }
+        if (regime & 2) {
+            // sorted order (what KMC / summarize.py emit): strictly increasing distinct codes, one random
+            // k-mer out of every block of `gap` consecutive ones; assumes < 2^31 rows per table
+            const uint64_t gap = bits > 31 ? (1ull << (bits - 31)) : 1ull;
+            code = (row * gap + (gap > 1 ? code % gap : 0ull)) & mask;
+        }
         const uint64_t hs = rng_u64(uint64_t(seed), row, 1);
         if (int(hs % 1000) < start_permille) {
             const uint64_t ns = 1 + (hs >> 20) % uint64_t(lag);
@@ -233,7 +239,7 @@ __global__ void synth_table_kernel(uint64_t* __restrict__ kmers, uint32_t* __res
         uint32_t c[5] = {0, 0, 0, 0, 0};
         const uint64_t h0 = rng_u64(uint64_t(seed), row, 2);
         const int dom = int(h0 & 3);
-        if (regime == 0) {
+        if ((regime & 1) == 0) {
             double u = u01(rng_u64(uint64_t(seed), row, 3));
             int N = 1;
             double p = 0.1353352832366127, cdf = p;     // Poisson(2)
@@ -382,7 +388,7 @@ extern "C" int bear_synth_table(uint64_t* d_kmers, uint32_t* d_counts, int64_t s
                                 int lag, int G, int64_t seed, int regime, int start_permille, void* stream) {
     const char* fn = "bear_synth_table";
     BEAR_REQUIRE(n >= 0 && stride >= n && lag >= 1 && lag <= 29 && G >= 1 && row_begin >= 0, fn);
-    BEAR_REQUIRE(regime == 0 || regime == 1, fn);
+    BEAR_REQUIRE(regime >= 0 && regime <= 3, fn);
     if (n == 0) return BEAR_OK;
     BEAR_REQUIRE(d_kmers && d_counts, fn);
     synth_table_kernel<<<blocks_for(n), THREADS, 0, ST(stream)>>>(d_kmers, d_counts, stride, row_begin, n, lag, G, seed,

@@ -13,7 +13,8 @@
 //   * log() is taken of running products spanning many rows, not once per row; the five reciprocals
 //     of a row share one division;
 //   * the weight-table gradient is scattered without atomics: rows are staged in shared memory and
-//     each chunk table is owned by one warp, which serialises intra-tile key collisions through a tag array.
+//     each chunk table is owned by one warp; key collisions inside a tile are resolved with a tag array and
+//     match.any, never with atomics.
 // Reductions are two-stage and deterministic across CTAs: per-CTA partials in the caller's workspace,
 // then a fixed-order sum.
 #include <math.h>
@@ -401,9 +402,10 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partials, int 
 // ------------------------------------------------------------------------------------------------
 // Per iteration a CTA handles NW tiles of 32 rows.  Phase A: every warp computes one tile (one row per
 // lane) and stages (k-mer payload, g_0..g_3) -- the gradient w.r.t. the logits -- in shared memory.
-// Phase B: warp ch owns gradient chunk table G[ch] (4 positions, 256 keys); it walks the NW staged tiles;
-// rows of a tile that collide on a key are serialised through a tag array, the winner does a plain
-// read-modify-write.  No atomics.
+// Phase B: warp ch owns gradient chunk table G[ch] (<= 4 positions, 256 keys); it walks the NW staged tiles;
+// a tag array picks one row per key for a plain read-modify-write, rows that lost (key collisions inside the
+// tile: rare for shuffled tables, the rule for the leading chunks of sorted ones) are combined per key
+// (match.any, butterfly sum when they all share one key) and applied by one lane per key.  No atomics.
 template <bool TRAIN_AR>
 __global__ void __launch_bounds__(THREADS, 2)
 linear_train_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ col, int64_t stride,
@@ -546,62 +548,74 @@ linear_train_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restri
         for (int b = 0; b < 4; ++b) stage_g[(warp * 4 + b) * 32 + lane] = g[b];
         __syncthreads();
         // ---------------- phase B: warp ch scatters chunk ch of every staged tile ----------------
-        // Rows of a tile with equal chunk keys collide on one table entry.  Each pending lane writes its
-        // id into tags[q]; whoever reads its own id back owns q this round and does a plain
-        // read-modify-write; the others retry (two rows of 32 rarely share one of 256 keys).
         for (int ch = warp; ch < nchg; ch += NW) {
             double* Gc = G + ch * COMBOS * 4;
             uint8_t* tg = tags + ch * COMBOS;
             const uint32_t kmask = chunk_mask(ch, ck);
-            const bool small_keys = kmask < uint32_t(COMBOS - 1);
             const int kshift = chunk_shift(lag, ch, ck);
             for (int t = 0; t < NW; ++t) {
                 const uint64_t k = stage_k[t * 32 + lane];
                 bool pending = k != KEY_INVALID;
                 if (!__any_sync(0xffffffffu, pending)) continue;
-                const int q = pending ? int(uint32_t(k >> kshift) & kmask) : 0;
+                const int q = pending ? int(uint32_t(k >> kshift) & kmask) : 0x7fffffff;
                 const double* sg = stage_g + t * 4 * 32;
-                double s0 = sg[lane], s1 = sg[32 + lane], s2 = sg[64 + lane], s3 = sg[96 + lane];
-                if (small_keys) {
-                    // few keys (chunk of < 4 positions): most rows collide, so combine equal keys first
-                    const unsigned grp = __match_any_sync(0xffffffffu, pending ? q : 0x7fffffff);
-                    if (pending && (__ffs(grp) - 1) == lane) {
-                        unsigned rest = grp & (grp - 1);
-                        while (rest) {
-                            const int j = __ffs(rest) - 1;
-                            rest &= rest - 1;
-                            s0 += sg[j];
-                            s1 += sg[32 + j];
-                            s2 += sg[64 + j];
-                            s3 += sg[96 + j];
-                        }
-                        double2* dst = reinterpret_cast<double2*>(Gc + q * 4);
-                        double2 a = dst[0], b2 = dst[1];
-                        a.x += s0;
-                        a.y += s1;
-                        b2.x += s2;
-                        b2.y += s3;
-                        dst[0] = a;
-                        dst[1] = b2;
-                    }
-                    __syncwarp();
-                    continue;
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                if (pending) {
+                    s0 = sg[lane];
+                    s1 = sg[32 + lane];
+                    s2 = sg[64 + lane];
+                    s3 = sg[96 + lane];
                 }
-                do {
-                    if (pending) tg[q] = uint8_t(lane);
-                    __syncwarp();
-                    if (pending && tg[q] == uint8_t(lane)) {
-                        double2* dst = reinterpret_cast<double2*>(Gc + q * 4);
-                        double2 a = dst[0], b2 = dst[1];
-                        a.x += s0;
-                        a.y += s1;
-                        b2.x += s2;
-                        b2.y += s3;
-                        dst[0] = a;
-                        dst[1] = b2;
-                        pending = false;
+                // Rows of a tile with equal keys collide on one table entry.  Round one: every pending lane
+                // writes its id into tags[q]; whoever reads its own id back owns q and does a plain
+                // read-modify-write.  With 256 random keys that settles nearly every row.
+                if (pending) tg[q] = uint8_t(lane);
+                __syncwarp();
+                if (pending && tg[q] == uint8_t(lane)) {
+                    double2* dst = reinterpret_cast<double2*>(Gc + q * 4);
+                    double2 a = dst[0], b2 = dst[1];
+                    a.x += s0;
+                    a.y += s1;
+                    b2.x += s2;
+                    b2.y += s3;
+                    dst[0] = a;
+                    dst[1] = b2;
+                    pending = false;
+                }
+                const unsigned left = __ballot_sync(0xffffffffu, pending);
+                if (left == 0) continue;
+                // Leftovers (always few for random keys; nearly the whole tile for the leading chunks of a
+                // sorted table or a chunk with few keys): combine equal keys, then one lane per key updates.
+                const unsigned grp = __match_any_sync(0xffffffffu, pending ? q : 0x7fffffff);
+                const bool leader = pending && (__ffs(grp) - 1) == lane;
+                if (__all_sync(0xffffffffu, !pending || grp == left)) {
+                    if (!pending) s0 = s1 = s2 = s3 = 0.0;
+                    s0 = warp_sum(s0);                 // one key for all leftovers: butterfly sum
+                    s1 = warp_sum(s1);
+                    s2 = warp_sum(s2);
+                    s3 = warp_sum(s3);
+                } else if (leader) {
+                    unsigned rest = grp & (grp - 1);
+                    while (rest) {
+                        const int j = __ffs(rest) - 1;
+                        rest &= rest - 1;
+                        s0 += sg[j];
+                        s1 += sg[32 + j];
+                        s2 += sg[64 + j];
+                        s3 += sg[96 + j];
                     }
-                } while (__any_sync(0xffffffffu, pending));
+                }
+                if (leader) {
+                    double2* dst = reinterpret_cast<double2*>(Gc + q * 4);
+                    double2 a = dst[0], b2 = dst[1];
+                    a.x += s0;
+                    a.y += s1;
+                    b2.x += s2;
+                    b2.y += s3;
+                    dst[0] = a;
+                    dst[1] = b2;
+                }
+                __syncwarp();
             }
         }
         if (warp == (nchg < NW ? nchg : 0)) {       // owner of gmat: the first warp without a chunk table

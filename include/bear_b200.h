@@ -205,7 +205,8 @@ int bear_adam_update(double* d_params, const double* d_grads, double* d_m, doubl
 
 /* Deterministic synthetic packed table for benchmarks and large-scale parity checks: rows
  * [row_begin, row_begin+n) of the table defined by (seed, lag, G, regime) -- see DESIGN.md.
- * regime 0 = sparse counts (N = 1 + Poisson(2)), 1 = dense counts (N ~ LogNormal(ln 300, 1.5)).
+ * regime bit 0: 0 = sparse counts (N = 1 + Poisson(2)), 1 = dense counts (N ~ LogNormal(ln 300, 1.5));
+ * regime bit 1: 0 = pseudo-random row order (shuffled table), 1 = rows sorted by k-mer (KMC order).
  * d_kmers[n], d_counts[G][5][stride] (row i of the output = table row row_begin + i). */
 int bear_synth_table(uint64_t* d_kmers, uint32_t* d_counts, int64_t stride, int64_t row_begin, int64_t n,
                      int lag, int G, int64_t seed, int regime, int start_permille, void* stream);

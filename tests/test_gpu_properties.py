@@ -135,3 +135,29 @@ def test_synthetic_subsample_matches_oracle(cuda, regime):
     want = O.evaluation([(oh, f, counts[:, 1], counts[:, 0])], torch.tensor(2.0, dtype=torch.float64), np.array([0.1, 1.0]))
     for g, w in zip(got, want):
         assert np.max(np.abs(g.numpy() - w.numpy())) <= 1e-10 * max(np.max(np.abs(w.numpy())), 1e-300)
+
+
+def test_sorted_table_matches_oracle_and_is_additive(cuda):
+    """Tables in KMC order (rows sorted by k-mer) make whole tiles share the leading chunk keys: the
+    uniform-key path of the gradient scatter must agree with the oracle too."""
+    from oracle import bear_oracle as O
+    K, lag = 4096, 20
+    table = synth(cuda, K, lag, 1, 2)
+    k, c = table.device_tensors()
+    codes = (k[:K] & ((1 << 58) - 1)).cpu().numpy()
+    assert np.all(np.diff(codes[(k[:K] >> 58).cpu().numpy() == 0]) > 0)
+    kmers = [s.decode() for s in table.kmers_str()]
+    counts = c[:, :, :K].permute(2, 0, 1).cpu().numpy().astype(np.float64)
+    gen = torch.Generator().manual_seed(6)
+    mat = O.init_linear(lag, 4, gen)[0] * 10
+    hs = torch.tensor(-0.2, dtype=torch.float64)
+    flat = train_step(table, 0, 0, K, mat.to(cuda), hs.reshape(1).to(cuda)).cpu()
+    loss, _, grads = O.train_step_grads(O.one_hot(kmers), torch.tensor(counts[:, 0]), hs, [mat], 'linear', K, False)
+    assert abs(float(flat[0]) - float(loss)) <= 1e-10 * abs(float(loss))
+    gw = grads[1].reshape(-1)
+    assert float((flat[2:] - gw).abs().max()) <= 1e-8 * float(gw.abs().max())
+    big = synth(cuda, 1 << 20, lag, 1, 2)
+    a = train_step(big, 0, 0, 1 << 20, mat.to(cuda), hs.reshape(1).to(cuda))
+    b = train_step(big, 0, 0, 300000, mat.to(cuda), hs.reshape(1).to(cuda)) + \
+        train_step(big, 0, 300000, (1 << 20) - 300000, mat.to(cuda), hs.reshape(1).to(cuda))
+    assert float((a - b).abs().max()) <= 1e-11 * float(a.abs().max())

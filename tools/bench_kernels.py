@@ -42,7 +42,8 @@ def main():
                     'achieved_gbs': gbs, 'frac_of_measured_hbm_peak': gbs / peak, 'note': note})
         print(json.dumps(out[-1]), flush=True)
 
-    for lag, G, regime, tag in ((20, 1, 0, 'C5 sparse lag20 G1'), (13, 8, 0, 'C3 sparse lag13 G8'), (10, 2, 1, 'C2 dense lag10 G2')):
+    for lag, G, regime, tag in ((20, 1, 0, 'C5 sparse lag20 G1'), (20, 1, 2, 'C5 sparse lag20 G1 SORTED rows'),
+                                (13, 8, 0, 'C3 sparse lag13 G8'), (10, 2, 1, 'C2 dense lag10 G2')):
         n = K // G if G > 1 else K
         stride = (n + 3) // 4 * 4
         kmers = torch.empty(stride, dtype=torch.int64, device=dev)
