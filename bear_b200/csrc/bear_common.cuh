@@ -179,35 +179,4 @@ static __device__ __noinline__ double rng_normal(uint64_t seed, uint64_t a, uint
     return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
 }
 
-// argmax of v[0..n) + sigma * N(0,1) (core.py:69-71,134-136).  When the top-2 gap exceeds
-// 16 sigma the noise cannot change the result (P < 1e-28) and is not generated.  seed < 0: no noise,
-// first maximum wins (tf.argmax semantics).
-template <int N>
-__device__ __forceinline__ int noisy_argmax(const double (&v)[N], double sigma, int64_t seed,
-                                            uint64_t row, uint64_t model) {
-    int best = 0;
-    double top = v[0], second = -INFINITY;
-#pragma unroll
-    for (int b = 1; b < N; ++b) {
-        if (v[b] > top) {
-            second = top;
-            top = v[b];
-            best = b;
-        } else if (v[b] > second) {
-            second = v[b];
-        }
-    }
-    if (seed < 0 || top - second > 16.0 * sigma) return best;
-    double nb = -INFINITY;
-#pragma unroll
-    for (int b = 0; b < N; ++b) {
-        const double x = v[b] + sigma * rng_normal(uint64_t(seed), row, model * 64 + uint64_t(b));
-        if (x > nb) {
-            nb = x;
-            best = b;
-        }
-    }
-    return best;
-}
-
 }  // namespace bear

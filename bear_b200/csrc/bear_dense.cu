@@ -28,16 +28,25 @@ __device__ __forceinline__ int decode_symbol(uint64_t code, int j, int lag, int 
     return j < nstart ? 4 : int((code >> (2 * (lag - 1 - j))) & 3u);
 }
 
-// core.tf_one_hot (core.py:156-174) from packed codes
+// core.tf_one_hot (core.py:156-174) from packed codes.  One thread per pair of output doubles so that a
+// warp writes 512 contiguous bytes (the output is 40 * lag bytes per k-mer, all of it stores).
 __global__ void decode_onehot_kernel(const uint64_t* __restrict__ kmers, int64_t n, int lag, int alphabet, int A1,
                                      double* __restrict__ out) {
-    const int64_t total = n * lag;
-    for (int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += int64_t(gridDim.x) * blockDim.x) {
-        const int64_t i = idx / lag;
-        const int j = int(idx - i * lag);
-        const int s = decode_symbol(kmers[i], j, lag, alphabet);
-        double* o = out + idx * A1;
-        for (int b = 0; b < A1; ++b) o[b] = (b == s) ? 1.0 : 0.0;
+    const int64_t per_row = int64_t(lag) * A1;
+    const int64_t total = n * per_row;
+    const int64_t pairs = (total + 1) / 2;
+    for (int64_t pidx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; pidx < pairs; pidx += int64_t(gridDim.x) * blockDim.x) {
+        double v[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int64_t e = 2 * pidx + h;
+            const int64_t i = e / per_row;
+            const int r = int(e - i * per_row);
+            const int j = r / A1, b = r - j * A1;
+            v[h] = (e < total && decode_symbol(__ldg(kmers + (i < n ? i : n - 1)), j, lag, alphabet) == b) ? 1.0 : 0.0;
+        }
+        if (2 * pidx + 1 < total) *reinterpret_cast<double2*>(out + 2 * pidx) = make_double2(v[0], v[1]);
+        else out[2 * pidx] = v[0];
     }
 }
 
@@ -287,7 +296,7 @@ extern "C" int bear_decode_onehot(const uint64_t* d_kmers, int64_t n, int lag, i
     BEAR_REQUIRE(bear_alphabet_size(alphabet) > 0 && lag >= 1 && lag <= bear_max_lag(alphabet) && n >= 0, fn);
     if (n == 0) return BEAR_OK;
     BEAR_REQUIRE(d_kmers && d_onehot, fn);
-    decode_onehot_kernel<<<blocks_for(n * lag), THREADS, 0, ST(stream)>>>(d_kmers, n, lag, alphabet, bear_alphabet_size(alphabet) + 1, d_onehot);
+    decode_onehot_kernel<<<blocks_for((n * lag * (bear_alphabet_size(alphabet) + 1) + 1) / 2), THREADS, 0, ST(stream)>>>(d_kmers, n, lag, alphabet, bear_alphabet_size(alphabet) + 1, d_onehot);
     BEAR_LAUNCH_CHECK("decode_onehot_kernel");
     return BEAR_OK;
 }

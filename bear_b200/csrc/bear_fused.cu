@@ -566,23 +566,28 @@ linear_train_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restri
                     s2 = sg[64 + lane];
                     s3 = sg[96 + lane];
                 }
-                // Rows of a tile with equal keys collide on one table entry.  Round one: every pending lane
+                // Rows of a tile with equal keys collide on one table entry.  Two tag rounds: every pending lane
                 // writes its id into tags[q]; whoever reads its own id back owns q and does a plain
-                // read-modify-write.  With 256 random keys that settles nearly every row.
-                if (pending) tg[q] = uint8_t(lane);
-                __syncwarp();
-                if (pending && tg[q] == uint8_t(lane)) {
-                    double2* dst = reinterpret_cast<double2*>(Gc + q * 4);
-                    double2 a = dst[0], b2 = dst[1];
-                    a.x += s0;
-                    a.y += s1;
-                    b2.x += s2;
-                    b2.y += s3;
-                    dst[0] = a;
-                    dst[1] = b2;
-                    pending = false;
+                // read-modify-write.  With 256 random keys that settles all but a few percent of the tiles.
+                unsigned left = 0;
+#pragma unroll
+                for (int round = 0; round < 2; ++round) {
+                    if (pending) tg[q] = uint8_t(lane);
+                    __syncwarp();
+                    if (pending && tg[q] == uint8_t(lane)) {
+                        double2* dst = reinterpret_cast<double2*>(Gc + q * 4);
+                        double2 a = dst[0], b2 = dst[1];
+                        a.x += s0;
+                        a.y += s1;
+                        b2.x += s2;
+                        b2.y += s3;
+                        dst[0] = a;
+                        dst[1] = b2;
+                        pending = false;
+                    }
+                    left = __ballot_sync(0xffffffffu, pending);
+                    if (left == 0) break;
                 }
-                const unsigned left = __ballot_sync(0xffffffffu, pending);
                 if (left == 0) continue;
                 // Leftovers (always few for random keys; nearly the whole tile for the leading chunks of a
                 // sorted table or a chunk with few keys): combine equal keys, then one lane per key updates.
