@@ -2,6 +2,12 @@
 // Replaces the tf.data text path of the reference: dataloader.dataloader (dataloader.py:6-50),
 // dataloader.sparse_dataloader (dataloader.py:52-109), core.tf_one_hot's symbol tables
 // (core.py:142-153) and the `wc -l` row count (models/train_bear_net.py:54-55).
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
 #include <cerrno>
 #include <cmath>
 #include <cstdarg>
@@ -9,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "bear_b200.h"
@@ -122,198 +129,321 @@ extern "C" int bear_decode_kmers(const uint64_t* h_kmers, int64_t n, int lag, in
 }
 
 // ---------------------------------------------------------------------------------------------
-// file reading
+// file reading: the file is mapped, cut into byte ranges at line boundaries, rows are counted per
+// range (pass 1) and parsed into their final slots (pass 2) by a pool of threads.
 // ---------------------------------------------------------------------------------------------
-struct LineReader {
-    FILE* fp = nullptr;
-    char* buf = nullptr;
-    size_t cap = 0;
-    ~LineReader() { if (fp) fclose(fp); free(buf); }
-    bool open(const char* path) { fp = fopen(path, "rb"); return fp != nullptr; }
-    // returns length without trailing newline / CR, or -1 at EOF
-    ssize_t next() {
-        ssize_t n = getline(&buf, &cap, fp);
-        if (n < 0) return -1;
-        while (n > 0 && (buf[n - 1] == '\n' || buf[n - 1] == '\r')) buf[--n] = 0;
-        return n;
+namespace {
+
+struct FileMap {
+    const char* data = nullptr;
+    size_t size = 0;
+    int fd = -1;
+    ~FileMap() {
+        if (data && size) munmap(const_cast<char*>(data), size);
+        if (fd >= 0) close(fd);
+    }
+    bool open_ro(const char* path) {
+        fd = ::open(path, O_RDONLY);
+        if (fd < 0) return false;
+        struct stat st;
+        if (fstat(fd, &st) != 0) return false;
+        size = size_t(st.st_size);
+        if (size == 0) return true;
+        void* m = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (m == MAP_FAILED) { size = 0; return false; }
+        data = static_cast<const char*>(m);
+        madvise(m, size, MADV_SEQUENTIAL);
+        return true;
     }
 };
 
-static bool blank(const char* s, ssize_t n) {
-    for (ssize_t i = 0; i < n; ++i) if (s[i] != ' ' && s[i] != '\t') return false;
+inline const char* line_end(const char* p, const char* e) {
+    const char* nl = static_cast<const char*>(memchr(p, '\n', size_t(e - p)));
+    return nl ? nl : e;
+}
+
+inline bool blank_line(const char* p, const char* e) {
+    for (; p < e; ++p)
+        if (*p != ' ' && *p != '\t' && *p != '\r') return false;
     return true;
 }
 
-extern "C" int64_t bear_count_rows(const char* path, int header) {
-    LineReader r;
-    if (!path || !r.open(path)) { bear_set_error("cannot open '%s': %s", path ? path : "(null)", strerror(errno)); return BEAR_ERR_IO; }
-    int64_t rows = 0;
-    bool skip = header != 0;
-    ssize_t n;
-    while ((n = r.next()) >= 0) {
-        if (blank(r.buf, n)) continue;
-        if (skip) { skip = false; continue; }
-        ++rows;
+// a cursor over one line [p, e)
+struct Cur {
+    const char* p;
+    const char* e;
+    void ws() { while (p < e && (*p == ' ' || *p == '\t' || *p == '\r')) ++p; }
+    bool eat(char c) { ws(); if (p < e && *p == c) { ++p; return true; } return false; }
+};
+
+int expect(Cur& c, char ch, const char* what) {
+    if (c.eat(ch)) return 0;
+    bear_set_error("expected '%c' in %s near '%.*s'", ch, what, int(std::min<ptrdiff_t>(20, c.e - c.p)), c.p);
+    return BEAR_ERR_PARSE;
+}
+
+// non-negative integer-valued JSON number -> uint32.  Plain digit strings take the fast path; anything
+// else (1.0, 3e0, -2, 2.5) goes through strtod on a bounded copy.
+int parse_count(Cur& c, uint32_t* out, const char* what) {
+    c.ws();
+    const char* s = c.p;
+    uint64_t v = 0;
+    int nd = 0;
+    while (s < c.e && *s >= '0' && *s <= '9' && nd < 11) { v = v * 10 + uint64_t(*s - '0'); ++s; ++nd; }
+    if (nd > 0 && nd < 11 && (s == c.e || (*s != '.' && *s != 'e' && *s != 'E'))) {
+        if (v > 4294967295ull) { bear_set_error("count %llu in %s exceeds uint32", (unsigned long long)v, what); return BEAR_ERR_RANGE; }
+        *out = uint32_t(v);
+        c.p = s;
+        return 0;
     }
-    return rows;
-}
-
-// parse a non-negative integer-valued number at *p (JSON number); advances *p.
-static int parse_count(const char** p, uint32_t* out, const char* what) {
+    char buf[48];
+    const size_t len = std::min<size_t>(sizeof(buf) - 1, size_t(c.e - c.p));
+    memcpy(buf, c.p, len);
+    buf[len] = 0;
     char* end = nullptr;
-    errno = 0;
-    double v = strtod(*p, &end);
-    if (end == *p) { bear_set_error("expected a number in %s near '%.20s'", what, *p); return BEAR_ERR_PARSE; }
-    if (!(v >= 0) || v != std::floor(v)) { bear_set_error("count %g in %s is negative or not an integer", v, what); return BEAR_ERR_PARSE; }
-    if (v > 4294967295.0) { bear_set_error("count %g in %s exceeds uint32", v, what); return BEAR_ERR_RANGE; }
-    *out = uint32_t(v);
-    *p = end;
+    const double d = strtod(buf, &end);
+    if (end == buf) { bear_set_error("expected a number in %s near '%.20s'", what, buf); return BEAR_ERR_PARSE; }
+    if (!(d >= 0) || d != std::floor(d)) { bear_set_error("count %g in %s is negative or not an integer", d, what); return BEAR_ERR_PARSE; }
+    if (d > 4294967295.0) { bear_set_error("count %g in %s exceeds uint32", d, what); return BEAR_ERR_RANGE; }
+    *out = uint32_t(d);
+    c.p += end - buf;
     return 0;
 }
 
-static void skip_ws(const char** p) { while (**p == ' ' || **p == '\t') ++*p; }
-
-static int expect(const char** p, char c, const char* what) {
-    skip_ws(p);
-    if (**p != c) { bear_set_error("expected '%c' in %s near '%.20s'", c, what, *p); return BEAR_ERR_PARSE; }
-    ++*p;
-    return 0;
-}
-
-struct PackArgs {
-    int alphabet, num_ds, A1;
+struct PackJob {
+    int alphabet, num_ds, A1, lag;
     int64_t first_row, max_rows, stride;
     uint64_t* kmers;
     uint32_t* counts;
-    int64_t rows = 0;
-    int lag = 0;
+    bool sparse;
 };
 
-static int check_args(const char* fn, const char* path, int alphabet, int num_ds, int64_t first_row,
-                      int64_t max_rows, const uint64_t* k, const uint32_t* c, int64_t stride,
-                      const int64_t* rows_out, const int* lag_out) {
-    if (!path || bear_alphabet_size(alphabet) < 0 || num_ds < 1 || first_row < 0 || max_rows < 0 ||
-        !k || !c || stride < max_rows || !rows_out || !lag_out) {
+int check_kmer(const PackJob& j, const char* s, int len, int64_t file_row, uint64_t* out) {
+    if (len != j.lag) {
+        bear_set_error("row %lld: k-mer length %d differs from %d", (long long)(file_row + 1), len, j.lag);
+        return BEAR_ERR_PARSE;
+    }
+    return encode_one(s, len, j.alphabet, out);
+}
+
+int parse_tsv_line(const PackJob& j, const char* b, const char* e, int64_t file_row, int64_t out_row) {
+    const char* tab = static_cast<const char*>(memchr(b, '\t', size_t(e - b)));
+    if (!tab) { bear_set_error("row %lld: no tab separator", (long long)(file_row + 1)); return BEAR_ERR_PARSE; }
+    int rc = check_kmer(j, b, int(tab - b), file_row, j.kmers + out_row);
+    if (rc) return rc;
+    Cur c{tab + 1, e};
+    if ((rc = expect(c, '[', "count matrix"))) return rc;
+    for (int g = 0; g < j.num_ds; ++g) {
+        if (g && (rc = expect(c, ',', "count matrix"))) return rc;
+        if ((rc = expect(c, '[', "count matrix"))) return rc;
+        for (int a = 0; a < j.A1; ++a) {
+            if (a && (rc = expect(c, ',', "count row"))) return rc;
+            if ((rc = parse_count(c, &j.counts[(int64_t(g) * j.A1 + a) * j.stride + out_row], "count row"))) return rc;
+        }
+        if ((rc = expect(c, ']', "count row (wrong alphabet size?)"))) return rc;
+    }
+    return expect(c, ']', "count matrix (wrong num_ds?)");
+}
+
+int parse_sparse_line(const PackJob& j, const char* b, const char* e, int64_t file_row, int64_t out_row) {
+    const char* s1 = static_cast<const char*>(memchr(b, ';', size_t(e - b)));
+    const char* s2 = s1 ? static_cast<const char*>(memchr(s1 + 1, ';', size_t(e - (s1 + 1)))) : nullptr;
+    if (!s1 || !s2) { bear_set_error("row %lld: expected 3 ';'-separated fields", (long long)(file_row + 1)); return BEAR_ERR_PARSE; }
+    const char* ks = b;
+    while (ks < s1 && *ks == ' ') ++ks;
+    const char* ke = s1;
+    while (ke > ks && ke[-1] == ' ') --ke;
+    int rc = check_kmer(j, ks, int(ke - ks), file_row, j.kmers + out_row);
+    if (rc) return rc;
+    for (int g = 0; g < j.num_ds; ++g)
+        for (int a = 0; a < j.A1; ++a) j.counts[(int64_t(g) * j.A1 + a) * j.stride + out_row] = 0;
+    // positions [[g,b],...] and values [v,...] are walked in lockstep
+    Cur pc{s1 + 1, s2}, vc{s2 + 1, e};
+    if ((rc = expect(pc, '[', "sparse positions")) || (rc = expect(vc, '[', "sparse values"))) return rc;
+    bool first = true;
+    for (;;) {
+        pc.ws();
+        if (!(pc.p < pc.e && *pc.p == '[')) break;
+        ++pc.p;
+        uint32_t g, a, v;
+        if ((rc = parse_count(pc, &g, "sparse positions")) || (rc = expect(pc, ',', "sparse positions")) ||
+            (rc = parse_count(pc, &a, "sparse positions")) || (rc = expect(pc, ']', "sparse positions"))) return rc;
+        if (int(g) >= j.num_ds || int(a) >= j.A1) {
+            bear_set_error("row %lld: sparse index [%u,%u] out of range", (long long)(file_row + 1), g, a);
+            return BEAR_ERR_PARSE;
+        }
+        if (!first && (rc = expect(vc, ',', "sparse values (length differs from positions?)"))) return rc;
+        if ((rc = parse_count(vc, &v, "sparse values"))) return rc;
+        uint32_t& cell = j.counts[(int64_t(g) * j.A1 + a) * j.stride + out_row];
+        if (uint64_t(cell) + v > 4294967295ull) { bear_set_error("row %lld: count exceeds uint32", (long long)(file_row + 1)); return BEAR_ERR_RANGE; }
+        cell += v;   // duplicate indices add
+        first = false;
+        pc.eat(',');
+    }
+    if ((rc = expect(pc, ']', "sparse positions"))) return rc;
+    return expect(vc, ']', "sparse values (length differs from positions?)");
+}
+
+struct Range {
+    const char* b;
+    const char* e;
+    int64_t rows = 0;        // non-blank lines in the range
+    int64_t first = 0;       // file row index of its first line
+    int rc = 0;
+    int64_t err_row = 0;
+    std::string err;
+};
+
+int num_threads_for(size_t bytes) {
+    if (bytes < (size_t(1) << 20)) return 1;
+    int n = int(std::thread::hardware_concurrency());
+    if (const char* env = getenv("BEAR_PACK_THREADS")) n = atoi(env);
+    n = std::max(1, std::min(n, 64));
+    return int(std::min<size_t>(size_t(n), bytes >> 18));
+}
+
+// splits [b, e) at line boundaries and counts the data rows of every piece
+std::vector<Range> split_and_count(const char* b, const char* e) {
+    const int nt = num_threads_for(size_t(e - b));
+    std::vector<Range> rs(nt);
+    const char* cur = b;
+    for (int t = 0; t < nt; ++t) {
+        const char* target = t == nt - 1 ? e : b + size_t(e - b) * size_t(t + 1) / size_t(nt);
+        const char* stop = target <= cur ? cur : (target >= e ? e : line_end(target, e) + (line_end(target, e) < e ? 1 : 0));
+        rs[t].b = cur;
+        rs[t].e = stop;
+        cur = stop;
+    }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t)
+        th.emplace_back([&rs, t] {
+            int64_t n = 0;
+            for (const char* p = rs[t].b; p < rs[t].e;) {
+                const char* le = line_end(p, rs[t].e);
+                if (!blank_line(p, le)) ++n;
+                p = le + 1;
+            }
+            rs[t].rows = n;
+        });
+    for (auto& x : th) x.join();
+    int64_t acc = 0;
+    for (auto& r : rs) { r.first = acc; acc += r.rows; }
+    return rs;
+}
+
+// start of the data (after the header line, if any)
+const char* skip_header(const char* b, const char* e, int header) {
+    if (!header) return b;
+    for (const char* p = b; p < e;) {
+        const char* le = line_end(p, e);
+        const bool bl = blank_line(p, le);
+        p = le < e ? le + 1 : e;
+        if (!bl) return p;
+    }
+    return e;
+}
+
+int pack_file(const char* fn, const char* path, int header, int alphabet, int num_ds, int64_t first_row, int64_t max_rows,
+              uint64_t* h_kmers, uint32_t* h_counts, int64_t stride, int64_t* rows_out, int* lag_out, bool sparse) {
+    if (!path || bear_alphabet_size(alphabet) < 0 || num_ds < 1 || first_row < 0 || max_rows < 0 || !h_kmers || !h_counts ||
+        stride < max_rows || !rows_out || !lag_out) {
         bear_set_error("%s: bad argument", fn);
         return BEAR_ERR_ARG;
     }
-    return 0;
+    FileMap fm;
+    if (!fm.open_ro(path)) { bear_set_error("cannot open '%s': %s", path, strerror(errno)); return BEAR_ERR_IO; }
+    const char* b = skip_header(fm.data, fm.data + fm.size, header);
+    const char* e = fm.data + fm.size;
+    *rows_out = 0;
+    *lag_out = 0;
+    if (b >= e || max_rows == 0) return BEAR_OK;
+    std::vector<Range> rs = split_and_count(b, e);
+    const int64_t total = rs.back().first + rs.back().rows;
+    if (total <= first_row) return BEAR_OK;
+    // the lag is the k-mer length of the first data row
+    PackJob job{alphabet, num_ds, bear_alphabet_size(alphabet) + 1, 0, first_row, max_rows, stride, h_kmers, h_counts, sparse};
+    for (const char* p = b; p < e;) {
+        const char* le = line_end(p, e);
+        if (!blank_line(p, le)) {
+            const char* sep = static_cast<const char*>(memchr(p, sparse ? ';' : '\t', size_t(le - p)));
+            const char* ks = p;
+            const char* ke = sep ? sep : le;
+            if (sparse) {
+                while (ks < ke && *ks == ' ') ++ks;
+                while (ke > ks && ke[-1] == ' ') --ke;
+            }
+            job.lag = int(ke - ks);
+            break;
+        }
+        p = le + 1;
+    }
+    if (job.lag < 1) { bear_set_error("row 1: empty k-mer"); return BEAR_ERR_PARSE; }
+    if (job.lag > bear_max_lag(alphabet)) {
+        bear_set_error("lag %d exceeds the packed layout's maximum %d", job.lag, bear_max_lag(alphabet));
+        return BEAR_ERR_RANGE;
+    }
+    std::vector<std::thread> th;
+    for (size_t t = 0; t < rs.size(); ++t)
+        th.emplace_back([&rs, &job, t] {
+            Range& r = rs[t];
+            int64_t file_row = r.first;
+            for (const char* p = r.b; p < r.e;) {
+                const char* le = line_end(p, r.e);
+                if (!blank_line(p, le)) {
+                    const int64_t out_row = file_row - job.first_row;
+                    if (out_row >= job.max_rows) return;
+                    if (out_row >= 0) {
+                        const char* end = le;
+                        while (end > p && end[-1] == '\r') --end;
+                        const int rc = job.sparse ? parse_sparse_line(job, p, end, file_row, out_row)
+                                                  : parse_tsv_line(job, p, end, file_row, out_row);
+                        if (rc) {
+                            r.rc = rc;
+                            r.err_row = file_row;
+                            r.err = bear_last_error();
+                            return;
+                        }
+                    }
+                    ++file_row;
+                }
+                p = le + 1;
+            }
+        });
+    for (auto& x : th) x.join();
+    for (const Range& r : rs)      // ranges are in file order: the first failing range holds the earliest error
+        if (r.rc) {
+            bear_set_error("%s", r.err.c_str());
+            return r.rc;
+        }
+    *rows_out = std::min(max_rows, total - first_row);
+    *lag_out = job.lag;
+    return BEAR_OK;
 }
 
-static int store_kmer(PackArgs& a, const char* s, int len, int64_t file_row) {
-    if (a.lag == 0) {
-        if (len < 1) { bear_set_error("row %lld: empty k-mer", (long long)file_row); return BEAR_ERR_PARSE; }
-        if (len > bear_max_lag(a.alphabet)) { bear_set_error("lag %d exceeds the packed layout's maximum %d", len, bear_max_lag(a.alphabet)); return BEAR_ERR_RANGE; }
-        a.lag = len;
-    } else if (len != a.lag) {
-        bear_set_error("row %lld: k-mer length %d differs from %d", (long long)file_row, len, a.lag);
-        return BEAR_ERR_PARSE;
-    }
-    return encode_one(s, len, a.alphabet, a.kmers + a.rows);
+}  // namespace
+
+extern "C" int64_t bear_count_rows(const char* path, int header) {
+    FileMap fm;
+    if (!path || !fm.open_ro(path)) { bear_set_error("cannot open '%s': %s", path ? path : "(null)", strerror(errno)); return BEAR_ERR_IO; }
+    const char* b = skip_header(fm.data, fm.data + fm.size, header);
+    const char* e = fm.data + fm.size;
+    if (b >= e) return 0;
+    const std::vector<Range> rs = split_and_count(b, e);
+    return rs.back().first + rs.back().rows;
 }
 
 extern "C" int bear_pack_tsv(const char* path, int header, int alphabet, int num_ds,
                              int64_t first_row, int64_t max_rows,
                              uint64_t* h_kmers, uint32_t* h_counts, int64_t stride,
                              int64_t* rows_out, int* lag_out) {
-    int rc = check_args("bear_pack_tsv", path, alphabet, num_ds, first_row, max_rows, h_kmers, h_counts, stride, rows_out, lag_out);
-    if (rc) return rc;
-    LineReader r;
-    if (!r.open(path)) { bear_set_error("cannot open '%s': %s", path, strerror(errno)); return BEAR_ERR_IO; }
-    PackArgs a{alphabet, num_ds, bear_alphabet_size(alphabet) + 1, first_row, max_rows, stride, h_kmers, h_counts};
-    bool skip = header != 0;
-    int64_t file_row = 0;
-    ssize_t n;
-    while (a.rows < max_rows && (n = r.next()) >= 0) {
-        if (blank(r.buf, n)) continue;
-        if (skip) { skip = false; continue; }
-        if (file_row++ < first_row) continue;
-        const char* tab = (const char*)memchr(r.buf, '\t', size_t(n));
-        if (!tab) { bear_set_error("row %lld: no tab separator", (long long)file_row); return BEAR_ERR_PARSE; }
-        if ((rc = store_kmer(a, r.buf, int(tab - r.buf), file_row))) return rc;
-        const char* p = tab + 1;
-        if ((rc = expect(&p, '[', "count matrix"))) return rc;
-        for (int g = 0; g < num_ds; ++g) {
-            if (g && (rc = expect(&p, ',', "count matrix"))) return rc;
-            if ((rc = expect(&p, '[', "count matrix"))) return rc;
-            for (int b = 0; b < a.A1; ++b) {
-                if (b && (rc = expect(&p, ',', "count row"))) return rc;
-                skip_ws(&p);
-                if ((rc = parse_count(&p, &h_counts[(int64_t(g) * a.A1 + b) * stride + a.rows], "count row"))) return rc;
-            }
-            if ((rc = expect(&p, ']', "count row (wrong alphabet size?)"))) return rc;
-        }
-        if ((rc = expect(&p, ']', "count matrix (wrong num_ds?)"))) return rc;
-        ++a.rows;
-    }
-    *rows_out = a.rows;
-    *lag_out = a.lag;
-    return BEAR_OK;
+    return pack_file("bear_pack_tsv", path, header, alphabet, num_ds, first_row, max_rows, h_kmers, h_counts, stride,
+                     rows_out, lag_out, false);
 }
 
 extern "C" int bear_pack_sparse(const char* path, int header, int alphabet, int num_ds,
                                 int64_t first_row, int64_t max_rows,
                                 uint64_t* h_kmers, uint32_t* h_counts, int64_t stride,
                                 int64_t* rows_out, int* lag_out) {
-    int rc = check_args("bear_pack_sparse", path, alphabet, num_ds, first_row, max_rows, h_kmers, h_counts, stride, rows_out, lag_out);
-    if (rc) return rc;
-    LineReader r;
-    if (!r.open(path)) { bear_set_error("cannot open '%s': %s", path, strerror(errno)); return BEAR_ERR_IO; }
-    PackArgs a{alphabet, num_ds, bear_alphabet_size(alphabet) + 1, first_row, max_rows, stride, h_kmers, h_counts};
-    bool skip = header != 0;
-    int64_t file_row = 0;
-    ssize_t n;
-    std::vector<std::pair<int, int>> pos;
-    while (a.rows < max_rows && (n = r.next()) >= 0) {
-        if (blank(r.buf, n)) continue;
-        if (skip) { skip = false; continue; }
-        if (file_row++ < first_row) continue;
-        const char* s1 = (const char*)memchr(r.buf, ';', size_t(n));
-        const char* s2 = s1 ? (const char*)memchr(s1 + 1, ';', size_t(n - (s1 + 1 - r.buf))) : nullptr;
-        if (!s1 || !s2) { bear_set_error("row %lld: expected 3 ';'-separated fields", (long long)file_row); return BEAR_ERR_PARSE; }
-        const char* ks = r.buf;
-        while (*ks == ' ') ++ks;
-        const char* ke = s1;
-        while (ke > ks && ke[-1] == ' ') --ke;
-        if ((rc = store_kmer(a, ks, int(ke - ks), file_row))) return rc;
-        for (int g = 0; g < num_ds; ++g)
-            for (int b = 0; b < a.A1; ++b) h_counts[(int64_t(g) * a.A1 + b) * stride + a.rows] = 0;
-        // positions [[g,b],...]
-        pos.clear();
-        const char* p = s1 + 1;
-        if ((rc = expect(&p, '[', "sparse positions"))) return rc;
-        skip_ws(&p);
-        while (*p == '[') {
-            ++p;
-            uint32_t g, b;
-            skip_ws(&p);
-            if ((rc = parse_count(&p, &g, "sparse positions"))) return rc;
-            if ((rc = expect(&p, ',', "sparse positions"))) return rc;
-            skip_ws(&p);
-            if ((rc = parse_count(&p, &b, "sparse positions"))) return rc;
-            if ((rc = expect(&p, ']', "sparse positions"))) return rc;
-            if (int(g) >= num_ds || int(b) >= a.A1) { bear_set_error("row %lld: sparse index [%u,%u] out of range", (long long)file_row, g, b); return BEAR_ERR_PARSE; }
-            pos.emplace_back(int(g), int(b));
-            skip_ws(&p);
-            if (*p == ',') { ++p; skip_ws(&p); }
-        }
-        if ((rc = expect(&p, ']', "sparse positions"))) return rc;
-        // values [v,...]
-        p = s2 + 1;
-        if ((rc = expect(&p, '[', "sparse values"))) return rc;
-        for (size_t i = 0; i < pos.size(); ++i) {
-            if (i && (rc = expect(&p, ',', "sparse values"))) return rc;
-            skip_ws(&p);
-            uint32_t v;
-            if ((rc = parse_count(&p, &v, "sparse values"))) return rc;
-            uint32_t& cell = h_counts[(int64_t(pos[i].first) * a.A1 + pos[i].second) * stride + a.rows];
-            if (uint64_t(cell) + v > 4294967295ull) { bear_set_error("row %lld: count exceeds uint32", (long long)file_row); return BEAR_ERR_RANGE; }
-            cell += v;   // duplicate indices add, as in tf.sparse.to_dense after reorder
-        }
-        if ((rc = expect(&p, ']', "sparse values (length differs from positions?)"))) return rc;
-        ++a.rows;
-    }
-    *rows_out = a.rows;
-    *lag_out = a.lag;
-    return BEAR_OK;
+    return pack_file("bear_pack_sparse", path, header, alphabet, num_ds, first_row, max_rows, h_kmers, h_counts, stride,
+                     rows_out, lag_out, true);
 }

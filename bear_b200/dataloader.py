@@ -138,6 +138,41 @@ class KmerTable:
             o += t.num_rows
         return cls(kmers, counts, K, t0.lag, t0.alphabet)
 
+    # -- packed binary shard cache ----------------------------------------------------------------
+    MAGIC = b'BEARPACK1\n'
+
+    def save(self, path):
+        """Write the packed table as one binary file (header + raw uint64 k-mers + raw uint32 counts) so that
+        later runs skip the text parse; ``KmerTable.load`` maps it back."""
+        import json
+        if self.kmers_host is None:
+            k, c = self._dev
+            kmers, counts = k.cpu().numpy().view(np.uint64), c.cpu().numpy().view(np.uint32)
+        else:
+            kmers, counts = self.kmers_host, self.counts_host
+        meta = json.dumps({'num_rows': self.num_rows, 'lag': self.lag, 'alphabet': self.alphabet, 'num_ds': self.num_ds,
+                           'A1': self.A1, 'stride': self.stride}).encode()
+        with open(path, 'wb') as fh:
+            fh.write(self.MAGIC)
+            fh.write(len(meta).to_bytes(8, 'little'))
+            fh.write(meta)
+            fh.write(b'\0' * (-fh.tell() % 64))
+            np.ascontiguousarray(kmers).tofile(fh)
+            np.ascontiguousarray(counts).tofile(fh)
+
+    @classmethod
+    def load(cls, path):
+        import json
+        with open(path, 'rb') as fh:
+            if fh.read(len(cls.MAGIC)) != cls.MAGIC:
+                raise ValueError('%s is not a BEARPACK file' % path)
+            meta = json.loads(fh.read(int.from_bytes(fh.read(8), 'little')))
+            off = fh.tell() + (-fh.tell() % 64)
+        stride, G, A1 = meta['stride'], meta['num_ds'], meta['A1']
+        kmers = np.memmap(path, dtype=np.uint64, mode='r', offset=off, shape=(stride,))
+        counts = np.memmap(path, dtype=np.uint32, mode='r', offset=off + 8 * stride, shape=(G, A1, stride))
+        return cls(kmers, counts, meta['num_rows'], meta['lag'], meta['alphabet'])
+
     def take(self, index):
         """Rows ``index`` (numpy int array) as a new host table."""
         index = np.asarray(index, dtype=np.int64)
@@ -155,9 +190,23 @@ class KmerTable:
         patterns are the uint64 / uint32 of the packed layout."""
         if self._dev is None:
             dev = _lib.device()
-            k = torch.from_numpy(self.kmers_host.view(np.int64)).pin_memory().to(dev, non_blocking=True)
-            c = torch.from_numpy(self.counts_host.view(np.int32)).pin_memory().to(dev, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            k = torch.empty(self.stride, dtype=torch.int64, device=dev)
+            c = torch.empty((self.num_ds, self.A1, self.stride), dtype=torch.int32, device=dev)
+            # upload through a bounded pinned staging buffer (tables can be larger than is sane to pin at once)
+            step = 1 << 24
+            kv, cv = self.kmers_host.view(np.int64), self.counts_host.view(np.int32).reshape(-1, self.stride)
+            stage = torch.empty(step, dtype=torch.int64).pin_memory()
+            s32 = stage.view(torch.int32)
+            cd = c.view(-1, self.stride)
+            for lo in range(0, self.stride, step):
+                hi = min(lo + step, self.stride)
+                stage[:hi - lo].copy_(torch.from_numpy(np.ascontiguousarray(kv[lo:hi])))
+                k[lo:hi].copy_(stage[:hi - lo], non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                for r in range(cv.shape[0]):
+                    s32[:hi - lo].copy_(torch.from_numpy(np.ascontiguousarray(cv[r, lo:hi])))
+                    cd[r, lo:hi].copy_(s32[:hi - lo], non_blocking=True)
+                    torch.cuda.current_stream().synchronize()
             self._dev = (k, c)
         return self._dev
 
@@ -282,6 +331,19 @@ def load_files(files, alphabet, batch_size, num_ds, sparse=False, header=None):
     tables = [KmerTable.from_file(f, alphabet, num_ds, sparse=sparse, header=header) for f in sorted(files)]
     table = tables[0] if len(tables) == 1 else KmerTable.concat(tables)
     return _local_shard(KmerDataset(table, batch_size))
+
+
+def pack_files(files, out_path, alphabet, num_ds, sparse=False, header=None):
+    """Parse text count files once (multi-threaded C++ packer) and write a BEARPACK binary shard."""
+    tables = [KmerTable.from_file(f, alphabet, num_ds, sparse=sparse, header=header) for f in sorted(files)]
+    table = tables[0] if len(tables) == 1 else KmerTable.concat(tables)
+    table.save(out_path)
+    return table
+
+
+def load_packed(path, batch_size):
+    """KmerDataset over a BEARPACK shard written by ``pack_files`` / ``KmerTable.save``."""
+    return _local_shard(KmerDataset(KmerTable.load(path), batch_size))
 
 
 def count_rows(file, header=False):

@@ -162,3 +162,53 @@ def test_dataset_batching_and_sharding_cover_every_row_once():
         assert sorted(sum(seen, [])) == sorted(t.kmers_str().tolist())
         per_batch = np.sum([[n for _, n, _ in ds.shard(r, world).batches()] for r in range(world)], 0)
         assert per_batch.tolist() == [300, 300, 300, 300, 165]
+
+
+def test_packed_binary_cache_round_trip(tmp_path):
+    """TSV -> BEARPACK shard -> memory-mapped table: bit-identical arrays and metadata."""
+    from bear_b200 import dataloader as dl
+    out = str(tmp_path / 'ysd1.bearpack')
+    t = dl.pack_files([YSD1], out, 'dna', 3)
+    u = dl.KmerTable.load(out)
+    assert (u.num_rows, u.lag, u.alphabet, u.num_ds, u.A1, u.stride) == (t.num_rows, t.lag, t.alphabet, t.num_ds, t.A1, t.stride)
+    assert np.array_equal(np.asarray(u.kmers_host), t.kmers_host) and np.array_equal(np.asarray(u.counts_host), t.counts_host)
+    ds = dl.KmerDataset(u, 500)
+    assert [n for _, n, _ in ds.batches()] == [500, 500, 365]
+    with pytest.raises(ValueError, match='not a BEARPACK'):
+        dl.KmerTable.load(YSD1)
+
+
+def test_multithreaded_pack_equals_single_thread(tmp_path, monkeypatch):
+    """The two-pass multi-threaded parse places every row exactly where the single-threaded one does,
+    honours first_row / max_rows windows and reports the earliest error."""
+    import ctypes
+    from bear_b200 import _lib, dataloader as dl
+    rng = np.random.default_rng(0)
+    lag, K = 11, 60000
+    lines = []
+    for i in range(K):
+        k = ''.join(rng.choice(list('ACGT'), size=lag))
+        c = rng.poisson(0.7, size=(2, 5))
+        lines.append(k + '\t[[' + ','.join(map(str, c[0])) + '],[' + ','.join(map(str, c[1])) + ']]')
+    path = _write(tmp_path, '\n'.join(lines) + '\n', 'big.tsv')
+    assert os.path.getsize(path) > (1 << 20)
+    monkeypatch.setenv('BEAR_PACK_THREADS', '1')
+    a = dl.KmerTable.from_file(path, 'dna', 2)
+    monkeypatch.setenv('BEAR_PACK_THREADS', '7')
+    b = dl.KmerTable.from_file(path, 'dna', 2)
+    assert a.num_rows == b.num_rows == K == dl.count_rows(path)
+    assert np.array_equal(a.kmers_host, b.kmers_host) and np.array_equal(a.counts_host, b.counts_host)
+    # a window of rows
+    kmers = np.zeros(1000, np.uint64)
+    counts = np.zeros((2, 5, 1000), np.uint32)
+    rows, lg = ctypes.c_int64(), ctypes.c_int()
+    _lib.check(_lib.lib.bear_pack_tsv(path.encode(), 0, 0, 2, 12345, 1000, _lib.ptr(kmers), _lib.ptr(counts), 1000,
+                                      ctypes.byref(rows), ctypes.byref(lg)))
+    assert rows.value == 1000 and lg.value == lag
+    assert np.array_equal(kmers, a.kmers_host[12345:13345]) and np.array_equal(counts, a.counts_host[:, :, 12345:13345])
+    # two malformed rows: the earlier one is reported
+    lines[40000] = lines[40000].replace('\t', ' ')
+    lines[20000] = 'ACGTNACGTAC' + lines[20000][lag:]
+    bad = _write(tmp_path, '\n'.join(lines) + '\n', 'bad.tsv')
+    with pytest.raises(_lib.BearError, match='outside the alphabet'):
+        dl.KmerTable.from_file(bad, 'dna', 2)

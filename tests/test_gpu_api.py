@@ -274,3 +274,22 @@ def test_lin_bear_config_converges_towards_published_table(cuda, tmp_path):
     assert 0.36 < float(r['heldout_accuracy_bear']) < 0.375
     assert float(r['h']) < 0.5
     assert float(r['heldout_perplex_ar']) > float(r['heldout_perplex_bear'])
+
+
+def test_packed_shard_cache_trains_identically(cuda, tmp_path):
+    """dataloader.pack_files / load_packed: a BEARPACK shard gives the same batches and the same training
+    result as parsing the TSV."""
+    from bear_b200 import ar_funcs, bear_net, dataloader
+    out = str(tmp_path / 'ysd1.bearpack')
+    dataloader.pack_files([YSD1], out, 'dna', 3)
+    a = dataloader.dataloader(YSD1, 'dna', 400, 3)
+    b = dataloader.load_packed(out, 400)
+    ka, ca = next(iter(a))
+    kb, cb = next(iter(b))
+    assert np.array_equal(ka.numpy(), kb.numpy()) and torch.equal(ca, cb)
+    torch.manual_seed(3)
+    p0, _, _ = bear_net._create_params(5, 4, ar_funcs.make_ar_func_linear, {})
+    p0 = [p.clone() for p in p0]
+    ra = bear_net.train(a, 1365, 1, 0, 'dna', 5, ar_funcs.make_ar_func_linear, {}, 0.01, 'Adam', False, params_restart=p0)
+    rb = bear_net.train(b, 1365, 1, 0, 'dna', 5, ar_funcs.make_ar_func_linear, {}, 0.01, 'Adam', False, params_restart=p0)
+    assert torch.allclose(ra[0][1], rb[0][1], rtol=1e-12, atol=0) and float(ra[1]) == pytest.approx(float(rb[1]), rel=1e-12)
