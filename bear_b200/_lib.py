@@ -59,6 +59,8 @@ _SIGNATURES = {
     'bear_loggamma_sample': (_i32, [_vp, _i64, _i64, _i64, _vp, _vp]),
     'bear_log_normalize': (_i32, [_vp, _i64, _i32, _vp]),
     'bear_synth_table': (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _i32, _i64, _i32, _i32, _vp]),
+    'bear_count_transitions': (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _i64, _vp, _vp]),
+    'bear_gather_table': (_i32, [_vp, _vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp]),
     'bear_adam_update': (_i32, [_vp, _vp, _vp, _vp, _i64, _f64, _f64, _f64, _f64, _vp, _vp]),
     'bear_ref_head': (_i32, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     'bear_ref_head_bwd': (_i32, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

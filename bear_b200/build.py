@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libbear_b200.so')
 STAMP = os.path.join(HERE, '.libbear_b200.stamp')
 
-SOURCES = ['bear_pack.cpp', 'bear_dense.cu', 'bear_fused.cu', 'bear_heads.cu']
+SOURCES = ['bear_pack.cpp', 'bear_dense.cu', 'bear_fused.cu', 'bear_heads.cu', 'bear_count.cu']
 HEADERS = ['bear_common.cuh', 'bear_host.h']
 
 NVCC_FLAGS = [

@@ -200,11 +200,11 @@ class KmerTable:
             cd = c.view(-1, self.stride)
             for lo in range(0, self.stride, step):
                 hi = min(lo + step, self.stride)
-                stage[:hi - lo].copy_(torch.from_numpy(np.ascontiguousarray(kv[lo:hi])))
+                stage[:hi - lo].copy_(torch.from_numpy(np.array(kv[lo:hi])))
                 k[lo:hi].copy_(stage[:hi - lo], non_blocking=True)
                 torch.cuda.current_stream().synchronize()
                 for r in range(cv.shape[0]):
-                    s32[:hi - lo].copy_(torch.from_numpy(np.ascontiguousarray(cv[r, lo:hi])))
+                    s32[:hi - lo].copy_(torch.from_numpy(np.array(cv[r, lo:hi])))
                     cd[r, lo:hi].copy_(s32[:hi - lo], non_blocking=True)
                     torch.cuda.current_stream().synchronize()
             self._dev = (k, c)

@@ -211,6 +211,24 @@ int bear_adam_update(double* d_params, const double* d_grads, double* d_m, doubl
 int bear_synth_table(uint64_t* d_kmers, uint32_t* d_counts, int64_t stride, int64_t row_begin, int64_t n,
                      int lag, int G, int64_t seed, int regime, int start_permille, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Device: building the count table from sequences (the table summarize.py emits; its definition is
+ * the brute-force count over '[' * lag + seq + ']' of tests/test_summarize.py:96-114).
+ * ---------------------------------------------------------------------------------------- */
+/* d_seq: all sequences concatenated (bytes, ACGT/U in either case); d_offsets[nseq+1]: start of each
+ * sequence; d_toff[nseq]: exclusive prefix sum of (len_i + 1), the transitions of each sequence;
+ * d_groups[nseq]: dataset group of each sequence; ntrans = sum(len_i + 1).  With reverse_complement
+ * the reverse complement of every sequence is counted too (summarize.py -r).  The hash table
+ * d_keys[cap] (initialised to all-ones) / d_counts[cap][G][5] (zeroed) has cap a power of two
+ * > distinct k-mers.  d_stats[3] += {distinct k-mers, skipped transitions (non-ACGT), count overflows}. */
+int bear_count_transitions(const uint8_t* d_seq, const int64_t* d_offsets, const int64_t* d_toff,
+                           const int32_t* d_groups, int64_t nseq, int64_t ntrans, int lag, int G,
+                           int reverse_complement, uint64_t* d_keys, uint32_t* d_counts, int64_t cap,
+                           uint64_t* d_stats, void* stream);
+/* Rows d_rows[n] (occupied slots of the hash table) -> packed table d_out_kmers[n], d_out_counts[G][5][stride]. */
+int bear_gather_table(const uint64_t* d_keys, const uint32_t* d_counts, const int64_t* d_rows, int64_t n, int G,
+                      int64_t stride, uint64_t* d_out_kmers, uint32_t* d_out_counts, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
