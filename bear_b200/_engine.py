@@ -7,6 +7,7 @@ flat float64 buffer ``[loss, d h_signed, d params...]`` (<= 52 KB), then the ide
 every rank.  Evaluation accumulates locally and allreduces its handful of scalars once at the end.
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -134,26 +135,67 @@ def check_dataset(data):
 # training
 # ---------------------------------------------------------------------------------------------
 def train_loop(data, num_kmers, ds_loc, train_ar, acc_steps, fp, optimizer_name, learning_rate, step_fn,
-               writer=None, loss_save=None):
+               writer=None, loss_save=None, graph_safe=False):
     """The loop of bear_net.train (bear_net.py:293-315): ``step_fn(r0, n, scale)`` adds the loss and
     gradients of one batch into ``fp.grad``; every ``acc_steps`` batches the buffer is allreduced,
-    the loss recorded and the optimizer applied."""
+    the loss recorded and the optimizer applied.
+
+    Small tables make this loop launch-bound (the reference's tutorial: 10 000 steps over 1 365 rows), so when
+    the step only launches libbear_b200 kernels (``graph_safe``) one epoch is captured in a CUDA graph
+    after an eager first epoch and replayed for the remaining ones (capture costs ~60 ms, so only runs of
+    >= 256 epochs use it)."""
     opt = Optimizer(optimizer_name, learning_rate, fp.total, fp.flat.device)
     fp.grad.zero_()
-    losses = []
-    step = 1
-    for r0, n, gB in data.batches():
-        step_fn(r0, n, float(num_kmers) / float(gB))
-        if step % acc_steps == 0:
-            allreduce_sum(fp.grad)
-            if writer is not None or loss_save is not None:
-                losses.append((step, (-fp.grad[0] / acc_steps).clone()))
-            opt.apply(fp.flat, fp.grad[1:])
-            fp.grad.zero_()
-        step += 1
-    if losses:
-        vals = torch.stack([v for _, v in losses]).cpu().tolist()     # one D2H copy at the end
-        for (s, _), v in zip(losses, vals):
+    record = writer is not None or loss_save is not None
+    nb, reps = len(data.ranges), data.repeats
+    steps_done, losses = 0, []          # losses: (first step index, tensor of -loss/acc_steps per update)
+
+    def one_epoch(loss_buf):
+        for i, ((r0, n), gB) in enumerate(zip(data.ranges, data.global_rows)):
+            step_fn(r0, n, float(num_kmers) / float(gB))
+            if (i + 1) % acc_steps == 0:
+                allreduce_sum(fp.grad)
+                if loss_buf is not None:
+                    loss_buf[(i + 1) // acc_steps - 1].copy_(-fp.grad[0] / acc_steps)
+                opt.apply(fp.flat, fp.grad[1:])
+                fp.grad.zero_()
+
+    use_graph = (graph_safe and fp.flat.is_cuda and world()[1] == 1 and reps >= 256 and 0 < nb <= 64
+                 and nb % acc_steps == 0 and not os.environ.get('BEAR_NO_GRAPH'))
+    if use_graph:
+        upd = nb // acc_steps
+        loss_buf = torch.zeros(upd, dtype=torch.float64, device=fp.flat.device)
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):           # eager first epoch (also warms up everything capture needs)
+            one_epoch(loss_buf)
+        cur.wait_stream(side)
+        losses.append(loss_buf.clone())
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            one_epoch(loss_buf)
+        for _ in range(1, reps):
+            graph.replay()
+            if record:
+                losses.append(loss_buf.clone())
+        flat_losses = torch.cat(losses) if record else None
+        update_steps = [(e * nb) + (u + 1) * acc_steps for e in range(reps) for u in range(upd)]
+    else:
+        vals, update_steps, step = [], [], 1
+        for r0, n, gB in data.batches():
+            step_fn(r0, n, float(num_kmers) / float(gB))
+            if step % acc_steps == 0:
+                allreduce_sum(fp.grad)
+                if record:
+                    vals.append((-fp.grad[0] / acc_steps).clone())
+                    update_steps.append(step)
+                opt.apply(fp.flat, fp.grad[1:])
+                fp.grad.zero_()
+            step += 1
+        flat_losses = torch.stack(vals) if vals else None
+    if record and flat_losses is not None:
+        for s, v in zip(update_steps, flat_losses.cpu().tolist()):     # one D2H copy at the end
             if loss_save is not None:
                 loss_save.append(v)
             if writer is not None and hasattr(writer, 'add_scalar'):

@@ -124,6 +124,7 @@ def train(data, num_kmers, epochs, ds_loc, alphabet, lag, make_ar_func, af_kwarg
     ws = eng.workspace(table, fp.total)
     k, c = table.device_tensors()
 
+    graph_safe = False
     if table.A1 != 5:
         # protein tables: dense route through the generic distribution kernels (any alphabet size)
         def step_fn(r0, n, scale):
@@ -134,6 +135,7 @@ def train(data, num_kmers, epochs, ds_loc, alphabet, lag, make_ar_func, af_kwarg
                 fp.grad[0] += _train_step(batch, scale * cn, h_signed, ar_func, params, grads, train_ar)
     elif eng.fused_linear_ok(ar_func, table):
         mat = params[1]
+        graph_safe = True            # the step is libbear_b200 launches only: capturable in a CUDA graph
 
         def step_fn(r0, n, scale):
             check(lib.bear_linear_train_step(ptr(k), table.col_ptr(ds_loc), table.stride, r0, n, table.lag,
@@ -148,7 +150,7 @@ def train(data, num_kmers, epochs, ds_loc, alphabet, lag, make_ar_func, af_kwarg
                                     lambda c0, cn: eng.explicit_f(ar_func, table, c0, cn))
 
     eng.train_loop(data, num_kmers, ds_loc, train_ar, acc_steps, fp, optimizer_name, learning_rate, step_fn,
-                   writer=writer, loss_save=loss_save)
+                   writer=writer, loss_save=loss_save, graph_safe=graph_safe and optimizer_name == 'Adam')
     for p in params:
         p.requires_grad_(False)
     return params, h_signed, ar_func

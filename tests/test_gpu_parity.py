@@ -385,3 +385,37 @@ def test_cnn_head_train_step_matches_oracle(cuda):
     for new, old, g in zip(params, p0, grads):          # SGD: new = old - lr * grad
         got_g = (old.cpu() - new.cpu()) / 0.01
         assert rel_err(got_g.numpy(), g.numpy()) <= 1e-7
+
+
+def test_cuda_graph_replay_matches_eager_loop(cuda, monkeypatch):
+    """Many epochs over a small table are replayed from a CUDA graph; the trajectory equals the eager loop
+    and the oracle's."""
+    import time
+    from bear_b200 import ar_funcs, bear_net, dataloader as dl
+    O = _oracle()
+    data = dl.dataloader(YSD1, 'dna', 700, 3)              # 2 batches per epoch
+    K = data.table.num_rows
+    torch.manual_seed(21)
+    p0, _, _ = bear_net._create_params(5, 4, ar_funcs.make_ar_func_linear, {})
+    p0 = [p.clone() for p in p0]
+    runs = {}
+    for mode in ('graph', 'eager'):
+        if mode == 'eager':
+            monkeypatch.setenv('BEAR_NO_GRAPH', '1')
+        ls = []
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        params, h_signed, _ = bear_net.train(data.repeat(300), K, 300, 0, 'dna', 5, ar_funcs.make_ar_func_linear, {}, 0.01,
+                                             'Adam', False, acc_steps=2, params_restart=p0, loss_save=ls)
+        torch.cuda.synchronize()
+        runs[mode] = (params[1].cpu(), float(h_signed), ls, time.perf_counter() - t0)
+    g, e = runs['graph'], runs['eager']
+    assert len(g[2]) == len(e[2]) == 300
+    assert rel_err(g[2], e[2]) <= 1e-10 and rel_err(g[0].numpy(), e[0].numpy()) <= 1e-8 and abs(g[1] - e[1]) <= 1e-9
+    kmers, counts = O.read_tsv(YSD1, 3)
+    oh, c0 = O.one_hot(kmers), torch.tensor(counts[:, 0])
+    batches = [(oh[i:i + 700], c0[i:i + 700]) for i in range(0, K, 700)] * 20
+    wl = []
+    O.train(batches, K, 'linear', [p0[1].cpu()], p0[0].cpu(), 0.01, False, acc_steps=2, loss_save=wl)
+    assert rel_err(g[2][:20], wl) <= 1e-9
+    print('300 epochs x 2 batches: graph %.3f s, eager %.3f s' % (g[3], e[3]))
