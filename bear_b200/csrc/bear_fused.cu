@@ -932,7 +932,7 @@ eval_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ tes
 // BMM marginal likelihood, every group and alpha
 // ------------------------------------------------------------------------------------------------
 template <int NA1, int NV>
-__global__ void __launch_bounds__(THREADS, NA1 == 5 ? 4 : 1)
+__global__ void __launch_bounds__(THREADS, NA1 == 5 ? 3 : 1)
 bmm_kernel(const uint32_t* __restrict__ counts, int64_t stride, int64_t n, int G,
            const double* __restrict__ d_alpha, int V, double* __restrict__ partials) {
     __shared__ double red[32];
@@ -989,10 +989,20 @@ bmm_kernel(const uint32_t* __restrict__ counts, int64_t stride, int64_t n, int G
     // four rows per thread with 128-bit loads when the column is 16-byte aligned (row0 % 4 == 0)
     const bool vec = (reinterpret_cast<uintptr_t>(col) & 15) == 0 && (stride & 3) == 0;
     const int64_t nq = vec ? n / 4 : 0;
-    for (int64_t qd = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; qd < nq; qd += int64_t(gridDim.x) * blockDim.x) {
-        uint4 v[NA1];
+    // software pipeline: the loads of the next four rows are in flight while the current four are processed
+    const int64_t qstep = int64_t(gridDim.x) * blockDim.x;
+    int64_t qd = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    uint4 v[NA1], w[NA1];
+    if (qd < nq) {
 #pragma unroll
         for (int b = 0; b < NA1; ++b) v[b] = __ldg(reinterpret_cast<const uint4*>(col + b * stride) + qd);
+    }
+    for (; qd < nq; qd += qstep) {
+        const bool more = qd + qstep < nq;
+        if (more) {
+#pragma unroll
+            for (int b = 0; b < NA1; ++b) w[b] = __ldg(reinterpret_cast<const uint4*>(col + b * stride) + qd + qstep);
+        }
         uint32_t c[NA1];
 #pragma unroll
         for (int b = 0; b < NA1; ++b) c[b] = v[b].x;
@@ -1006,6 +1016,10 @@ bmm_kernel(const uint32_t* __restrict__ counts, int64_t stride, int64_t n, int G
 #pragma unroll
         for (int b = 0; b < NA1; ++b) c[b] = v[b].w;
         row_term(c);
+        if (more) {
+#pragma unroll
+            for (int b = 0; b < NA1; ++b) v[b] = w[b];
+        }
     }
     for (int64_t i = nq * 4 + int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
         uint32_t c[NA1];
