@@ -41,6 +41,71 @@ def fused_linear_ok(ar_func, table):
     return head_kind(ar_func) == 'linear' and table.alphabet in ('dna', 'rna')
 
 
+def cnn_dims(ar_func):
+    """(filter_width, num_filters, kmer_layer1_width) of a CNN head from its parameter shapes (ar_funcs.py:78-89)."""
+    filters, W1 = ar_func.params[0], ar_func.params[2]
+    return int(filters.shape[0]), int(filters.shape[2]), int(W1.shape[2])
+
+
+def fused_cnn_ok(ar_func, table):
+    """True when the CNN head runs in the hand-written fused kernels (bear_cnn_*): DNA / RNA table and
+    dimensions inside the kernels' envelope (F <= 32, H1 <= 16, tile fits shared memory)."""
+    if head_kind(ar_func) != 'cnn' or table.alphabet not in ('dna', 'rna') or os.environ.get('BEAR_CNN_TORCH'):
+        return False
+    W, F, H1 = cnn_dims(ar_func)
+    return bool(lib.bear_cnn_supported(table.lag, W, F, H1))
+
+
+def cnn_param_block(params):
+    """The eight CNN parameter arrays as one contiguous float64 block in the reference's list order
+    (ar_funcs.py:98-99).  Views of a FlatParams buffer already are one; anything else is concatenated."""
+    consecutive = all(p.is_contiguous() and p.dtype == torch.float64 for p in params) and all(
+        params[i + 1].data_ptr() == params[i].data_ptr() + 8 * params[i].numel() for i in range(len(params) - 1))
+    if consecutive:
+        n = sum(int(p.numel()) for p in params)
+        return torch.as_strided(params[0].detach(), (n,), (1,))
+    return torch.cat([p.detach().reshape(-1).to(torch.float64) for p in params]).contiguous()
+
+
+def cnn_forward(ar_func, table, r0, n, block=None):
+    """f[n, 5] = CNN head of rows [r0, r0+n) straight from the packed codes (bear_cnn_head_forward)."""
+    k, _ = table.device_tensors()
+    W, F, H1 = cnn_dims(ar_func)
+    if block is None:
+        block = cnn_param_block(ar_func.params)
+    f = torch.empty((n, table.A1), dtype=torch.float64, device=k.device)
+    check(lib.bear_cnn_head_forward(ptr(k), r0, n, table.lag, W, F, H1, ptr(block), ptr(f), _lib.stream()))
+    return f
+
+
+class _CnnPacked(torch.autograd.Function):
+    """Differentiable f = CNN(packed rows) for callers that put more torch / kernel stages after the head
+    (bear_ref embeds it as the net g, bear_ref.py:63-68): forward and backward are the fused kernels."""
+
+    @staticmethod
+    def forward(ctx, block, ar_func, table, r0, n):
+        ctx.args = (ar_func, table, r0, n)
+        ctx.save_for_backward(block)
+        return cnn_forward(ar_func, table, r0, n, block.detach().contiguous())
+
+    @staticmethod
+    def backward(ctx, gf):
+        ar_func, table, r0, n = ctx.args
+        block, = ctx.saved_tensors
+        k, _ = table.device_tensors()
+        W, F, H1 = cnn_dims(ar_func)
+        gblock = torch.zeros_like(block)
+        ws = workspace(table, block.numel())
+        check(lib.bear_cnn_head_backward(ptr(k), r0, n, table.lag, W, F, H1, ptr(block.detach().contiguous()),
+                                         ptr(gf.contiguous()), ptr(gblock), ptr(ws), _lib.stream()))
+        return gblock, None, None, None, None
+
+
+def cnn_forward_autograd(ar_func, table, r0, n):
+    block = torch.cat([p.reshape(-1) for p in ar_func.params])
+    return _CnnPacked.apply(block, ar_func, table, r0, n)
+
+
 class FlatParams:
     """[h_signed, params...] packed in one contiguous float64 device buffer.  The tensors handed to
     the user (and captured by plugin closures) are re-pointed to views of it, so the optimizer

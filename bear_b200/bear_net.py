@@ -9,8 +9,10 @@ Mirrors the reference's ``bear_model/bear_net.py`` entry points (``train`` bear_
 Hot path: with the built-in linear head on DNA/RNA each training batch is ONE fused kernel
 (``bear_linear_train_step``: 2-bit decode -> table-gather head -> lgamma/digamma forward+backward ->
 in-kernel reductions) that adds ``[loss, d h_signed, d mat]`` into a flat buffer; evaluation is
-``bear_eval_step``.  Other heads (CNN, user plugins) are evaluated with torch ops on the device and
-enter through ``bear_dm_train_step_explicit`` / ``BEAR_HEAD_EXPLICIT``.
+``bear_eval_step``.  The built-in CNN head is one fused kernel too (``bear_cnn_train_step``: conv as a
+gather, dense layers on the FP64 tensor cores, loss and the whole backward pass on-chip).  Other heads
+(user plugins, CNN shapes outside the fused kernel) are evaluated with torch ops on the device and enter
+through ``bear_dm_train_step_explicit`` / ``BEAR_HEAD_EXPLICIT``.
 """
 import numpy as np
 import torch
@@ -141,6 +143,16 @@ def train(data, num_kmers, epochs, ds_loc, alphabet, lag, make_ar_func, af_kwarg
             check(lib.bear_linear_train_step(ptr(k), table.col_ptr(ds_loc), table.stride, r0, n, table.lag,
                                              ptr(mat), ptr(h_signed), scale, int(train_ar), ptr(fp.grad), None,
                                              ptr(ws), _lib.stream()))
+    elif eng.fused_cnn_ok(ar_func, table):
+        W, F, H1 = eng.cnn_dims(ar_func)
+        block = eng.cnn_param_block(params[1:])      # views of fp.flat: contiguous, in the reference order
+        assert block.data_ptr() == params[1].data_ptr()
+        graph_safe = True
+
+        def step_fn(r0, n, scale):
+            check(lib.bear_cnn_train_step(ptr(k), table.col_ptr(ds_loc), table.stride, r0, n, table.lag, W, F, H1,
+                                          ptr(block), ptr(h_signed), scale, int(train_ar), ptr(fp.grad), None,
+                                          ptr(ws), _lib.stream()))
     else:
         for p in params[1:]:
             p.requires_grad_(True)
@@ -166,6 +178,9 @@ def _head_for_eval(ar_func, table):
     if eng.fused_linear_ok(ar_func, table):
         mat = ar_func.params[0].detach().contiguous()
         return _lib.HEAD_LINEAR, (lambda r0, n: (mat, ptr(mat)))
+    if eng.fused_cnn_ok(ar_func, table):
+        block = eng.cnn_param_block(ar_func.params)
+        return _lib.HEAD_EXPLICIT, eng.explicit_head_ptr_fn(lambda c0, cn: eng.cnn_forward(ar_func, table, c0, cn, block))
     return _lib.HEAD_EXPLICIT, eng.explicit_head_ptr_fn(lambda c0, cn: eng.explicit_f(ar_func, table, c0, cn))
 
 

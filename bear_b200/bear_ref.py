@@ -103,6 +103,8 @@ def _net_values(ar_func, table, r0, n):
     net = ar_func.net_func
     if eng.head_kind(net) == 'stop':
         return None
+    if eng.fused_cnn_ok(net, table):
+        return eng.cnn_forward_autograd(net, table, r0, n) if torch.is_grad_enabled() else eng.cnn_forward(net, table, r0, n)
     g = net(eng.onehot_rows(table, r0, n))
     return g.expand(n, -1) if g.dim() == 1 else g
 

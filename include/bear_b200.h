@@ -167,6 +167,34 @@ int bear_eval_step(const uint64_t* d_kmers, const uint32_t* d_test_col, const ui
                    const double* d_h /* [H] */, int H, const double* d_van /* [V] */, int V,
                    int64_t seed, double* d_acc, double* d_workspace, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Device: the CNN autoregressive head (ar_funcs.make_ar_func_cnn, ar_funcs.py:49-99) fused with the
+ * loss: conv1d as a gather -> layer norm -> elu -> dense (FP64 tensor cores) -> layer norm -> elu ->
+ * dense -> softmax, and its whole backward pass, in one kernel (DNA/RNA, A1 = 5).
+ * d_params: the eight parameter arrays concatenated in the reference's list order (ar_funcs.py:98-99):
+ *   filters[W,5,F], intercept0[P,F], weights1[P,F,H1], intercept1[H1], weights2[H1,5], intercept2[5],
+ *   scale0[P,F], scale1[H1]   with P = lag - W + 1;  bear_cnn_num_params() doubles in total.
+ * bear_cnn_supported() is 1 when the dimensions fit the fused kernels (F <= 32, H1 <= 16, tile in
+ * shared memory); otherwise the entry points return BEAR_ERR_RANGE and the head has to be evaluated by
+ * the caller (BEAR_HEAD_EXPLICIT / bear_dm_train_step_explicit).
+ * ---------------------------------------------------------------------------------------- */
+int bear_cnn_supported(int lag, int filter_width, int num_filters, int layer1_width);
+int64_t bear_cnn_num_params(int lag, int filter_width, int num_filters, int layer1_width);
+/* f[n, 5] = ar_func(k-mers row0..row0+n) (ar_funcs.py:91-97); row i of d_f = table row row0 + i */
+int bear_cnn_head_forward(const uint64_t* d_kmers, int64_t row0, int64_t n, int lag, int filter_width,
+                          int num_filters, int layer1_width, const double* d_params, double* d_f, void* stream);
+/* bear_net._train_step (bear_net.py:146-197) with the CNN head: same contract as bear_linear_train_step;
+ * adds [loss, d loss/d h_signed, d loss/d params (order of d_params)] into d_flat[0 .. 2+num_params). */
+int bear_cnn_train_step(const uint64_t* d_kmers, const uint32_t* d_col, int64_t stride, int64_t row0, int64_t n,
+                        int lag, int filter_width, int num_filters, int layer1_width, const double* d_params,
+                        const double* d_h_signed, double scale, int train_ar, double* d_flat, double* d_ll_out,
+                        double* d_workspace, void* stream);
+/* Backward of bear_cnn_head_forward for an upstream gradient d_gf[n, 5] (w.r.t. f): adds the parameter
+ * gradients into d_gparams[num_params] (used when the CNN is the embedded net of bear_ref, bear_ref.py:63-68). */
+int bear_cnn_head_backward(const uint64_t* d_kmers, int64_t row0, int64_t n, int lag, int filter_width,
+                           int num_filters, int layer1_width, const double* d_params, const double* d_gf,
+                           double* d_gparams, double* d_workspace, void* stream);
+
 /* dataloader._marginal_step / bmm_likelihood (dataloader.py:111-147) on the packed table:
  * adds sum_k lbeta(c + a_v) - lbeta(a_v) for every group and alpha into d_out[G, V]. */
 int bear_bmm_likelihood(const uint32_t* d_counts, int64_t stride, int64_t row0, int64_t n,

@@ -42,6 +42,49 @@ def main():
                     'achieved_gbs': gbs, 'frac_of_measured_hbm_peak': gbs / peak, 'note': note})
         print(json.dumps(out[-1]), flush=True)
 
+    only = os.environ.get('ONLY', '')
+
+    def cnn_section():
+        """C4: CNN head (filter_width 3, 30 filters, layer width 16), lag 13, 4 groups -- fused kernels vs the
+        torch-op explicit route (the plugin path) on the same rows."""
+        from bear_b200 import ar_funcs, _engine as eng, dataloader as dl
+        lag, G, W, F, H1 = 13, 4, 3, 30, 16
+        n = int(os.environ.get('CNN_ROWS', 1 << 22))
+        stride = (n + 3) // 4 * 4
+        kmers = torch.empty(stride, dtype=torch.int64, device=dev)
+        counts = torch.empty((G, 5, stride), dtype=torch.int32, device=dev)
+        check(lib.bear_synth_table(ptr(kmers), ptr(counts), stride, 0, n, lag, G, 24, 1, 10, _lib.stream()))
+        table = dl.KmerTable.from_device(kmers, counts, n, lag, 'dna')
+        torch.manual_seed(0)
+        af, params = ar_funcs.make_ar_func_cnn(lag, 4, filter_width=W)
+        block = torch.cat([p.reshape(-1) for p in params]).contiguous()
+        npar = block.numel()
+        ws = torch.empty(lib.bear_workspace_doubles(n, lag, npar), dtype=torch.float64, device=dev)
+        hs = torch.zeros(1, dtype=torch.float64, device=dev)
+        flat = torch.zeros(2 + npar, dtype=torch.float64, device=dev)
+        flops = 3 * 2 * (lag - W + 1) * F * H1        # three dense-layer-1 contractions per row
+        for ar in (0, 1):
+            t = timed(lambda: check(lib.bear_cnn_train_step(ptr(kmers), ptr(counts), stride, 0, n, lag, W, F, H1, ptr(block), ptr(hs),
+                                                            1.0, ar, ptr(flat), None, ptr(ws), _lib.stream())), reps=3, warm=1)
+            report('cnn_kernel<TRAIN_%s> [C4 dense lag13 G4 W3 F30 H16]' % ('AR' if ar else 'BEAR'), t, n, 28,
+                   'compute-bound: %.2f TFLOP/s of FP64 tensor-core work (dense layer 1 fwd + 2 bwd)' % (flops * n / t / 1e12))
+        f = torch.empty((n, 5), dtype=torch.float64, device=dev)
+        t = timed(lambda: check(lib.bear_cnn_head_forward(ptr(kmers), 0, n, lag, W, F, H1, ptr(block), ptr(f), _lib.stream())), reps=3, warm=1)
+        report('cnn_kernel<FWD> [C4 dense lag13 G4 W3 F30 H16]', t, n, 48, 'reads 8 B k-mer, writes 40 B f')
+        m = min(n, 1 << 20)
+        fp = eng.FlatParams([hs.reshape(())] + [p.requires_grad_(True) for p in params])
+
+        def torch_route():
+            eng.explicit_train_step(table, 0, 0, m, 1.0, False, fp, ws, lambda c0, cn: eng.explicit_f(af, table, c0, cn))
+        t = timed(torch_route, reps=2, warm=1)
+        report('torch-op explicit route, CNN train step [C4 dense lag13 G4 W3 F30 H16]', t, m, 28,
+               'plugin path: decode_onehot -> torch ops -> bear_dm_train_step_explicit -> autograd')
+
+    if only in ('', 'cnn'):
+        cnn_section()
+    if only == 'cnn':
+        return
+
     for lag, G, regime, tag in ((20, 1, 0, 'C5 sparse lag20 G1'), (20, 1, 2, 'C5 sparse lag20 G1 SORTED rows'),
                                 (13, 8, 0, 'C3 sparse lag13 G8'), (10, 2, 1, 'C2 dense lag10 G2')):
         n = K // G if G > 1 else K
