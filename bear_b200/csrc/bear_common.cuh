@@ -110,6 +110,31 @@ struct LogProd {
     __device__ __forceinline__ void push(const LgDg& t) { push(t.add, t.mul); }
 };
 
+// Long-running variant for per-thread accumulators spanning many rows: when the running product leaves
+// [1e-40, 1e40] its binary exponent is moved into an integer (a handful of integer instructions) instead
+// of calling log(); value() = add + ex ln 2 + log(mul).
+struct LogProdLong {
+    double add = 0.0, mul = 1.0;
+    int ex = 0;
+    __device__ __forceinline__ void push(double a, double m) {
+        add += a;
+        if (mul > 1e40 || mul < 1e-40) {
+            if (mul > 1e-300 && mul < 1e300) {
+                const int hi = __double2hiint(mul);
+                ex += ((hi >> 20) & 0x7ff) - 1023;
+                mul = __hiloint2double((hi & 0x800fffff) | 0x3ff00000, __double2loint(mul));
+            } else {                       // zero / subnormal / inf: keep the reference's -inf / inf
+                add += log(mul);
+                mul = 1.0;
+            }
+        }
+        mul *= m;
+    }
+    __device__ __forceinline__ double value() const {
+        return add + (double(ex) * 0.69314718055994530942 + (mul == 1.0 ? 0.0 : log(mul)));
+    }
+};
+
 // numerator / denominator pair: value = num - den
 __device__ __forceinline__ double logprod_diff(const LogProd& num, const LogProd& den) {
     // both |log10 mul| <= 140 by construction, so the ratio cannot overflow
