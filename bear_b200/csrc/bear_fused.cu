@@ -1,24 +1,24 @@
 // Fused packed-path kernels (DNA/RNA, A1 = 5): the count-streaming hot path.
-//   linear_train_kernel   bear_net._train_step (bear_net.py:146-197) + ar_funcs.make_ar_func_linear
+//   linear_train2_kernel  bear_net._train_step (bear_net.py:146-197) + ar_funcs.make_ar_func_linear
 //                         (ar_funcs.py:23-46) + core.*.counts_log_prob (core.py:73-74,138-139), fwd+bwd
-//   explicit_train_kernel the same loss for a caller-evaluated head f (CNN / bear_ref / plugins)
+//   explicit_train_kernel the same loss for a caller-evaluated head f (bear_ref / plugins)
 //   eval_kernel           bear_net._evaluation_step (bear_net.py:323-371), h_scan (bear_net.py:516-531)
 //   bmm_kernel            dataloader._marginal_step (dataloader.py:111-113)
 // Every kernel streams the packed table once (8 B k-mer + 20 B per count column per row) and keeps all
 // per-row temporaries in registers.  What makes the sparse-count regime cheap:
-//   * the linear head is a gather from per-chunk tables of exp-ratios (4 positions per lookup);
+//   * the linear head is a gather from per-chunk tables of exp-ratios (4 positions per lookup); the tables
+//     also hold the start-padded patterns, so every k-mer takes the same path;
 //   * lgamma / digamma differences at small integer offsets are rising factorials evaluated with
 //     predicated straight-line code; terms that do not depend on the row's k-mer (the "total" term of
 //     the Dirichlet-multinomial, BMM priors) come from per-CTA tables indexed by the count;
 //   * log() is taken of running products spanning many rows, not once per row; the five reciprocals
 //     of a row share one division;
-//   * the weight-table gradient is scattered without atomics: rows are staged in shared memory and
-//     each chunk table is owned by one warp; key collisions inside a tile are resolved with a tag array and
-//     match.any, never with atomics.
+//   * the weight-table gradient is scattered without atomics: producer warps stage rows in shared memory,
+//     each gradient chunk table is owned by one consumer warp, rows with equal keys are ranked by the
+//     producer (match.any) and applied in separate read-modify-write rounds.
 // Reductions are two-stage and deterministic across CTAs: per-CTA partials in the caller's workspace,
 // then a fixed-order sum.
 #include <math.h>
-#include <stdlib.h>
 
 #include "bear_b200.h"
 #include "bear_common.cuh"
@@ -30,14 +30,10 @@ namespace {
 using namespace bear;
 
 constexpr int CHUNK = 4;         // at most 4 positions per chunk table (forward ratios R, gradient G)
-constexpr int COMBOS = 256;      // 4^CHUNK
 constexpr int THREADS = 256;
-constexpr int NW = THREADS / 32;
 constexpr int MAX_GRID = 148 * 4;
 constexpr int TABN = 64;         // counts below TABN index the per-CTA tables of row-independent terms
 constexpr uint64_t PAYLOAD_MASK = (1ull << 58) - 1;
-constexpr uint64_t KEY_INVALID = ~0ull;
-constexpr int SLOWCAP = 8;       // start-padded rows per tile that are staged (more fall back to atomics)
 
 __host__ __device__ inline int num_chunks(int lag) { return (lag + CHUNK - 1) / CHUNK; }
 
@@ -57,112 +53,9 @@ __host__ __device__ inline ChunkGeom chunk_geom(int lag, int nch, int ch) {
     return g;
 }
 
-
-// Chunk tables of the linear head.  For chunk ch (positions 4ch..4ch+3) and symbol combination q,
-// R[ch][q][b] = exp(l_b - l_4), b < 4, with l = sum of the chunk's rows of `mat`.  The softmax of a
-// start-free k-mer is then prod_ch R[ch][q_ch][b] / (1 + sum_b prod_ch R[ch][q_ch][b]).
-__device__ void build_ratio_tables(const double* smat, double* R, int lag) {
-    const int nch = num_chunks(lag);
-    for (int idx = threadIdx.x; idx < nch * COMBOS; idx += blockDim.x) {
-        const int ch = idx >> 8, q = idx & 255;
-        const ChunkGeom cg = chunk_geom(lag, nch, ch);
-        const int r = cg.size;
-        double l[A1] = {0, 0, 0, 0, 0};
-        if (q < (1 << (2 * r))) {
-            for (int p = 0; p < r; ++p) {
-                const int s = (q >> (2 * (r - 1 - p))) & 3;
-                const double* row = smat + ((cg.start + p) * A1 + s) * A1;
-#pragma unroll
-                for (int b = 0; b < A1; ++b) l[b] += row[b];
-            }
-        }
-#pragma unroll
-        for (int b = 0; b < 4; ++b) R[idx * 4 + b] = exp(l[b] - l[4]);
-    }
-}
-
-__device__ __forceinline__ int chunk_shift(int lag, int ch, const ChunkKeys& ck) {
-    const int size = ck.base + (ch < ck.extra ? 1 : 0);
-    const int start = ch * ck.base + (ch < ck.extra ? ch : ck.extra);
-    return 2 * (lag - start - size);
-}
-__device__ __forceinline__ uint32_t chunk_mask(int ch, const ChunkKeys& ck) {
-    return (1u << (2 * (ck.base + (ch < ck.extra ? 1 : 0)))) - 1u;
-}
-
 __device__ __forceinline__ int symbol_at(uint64_t v, int j, int lag, int nstart) {
     return j < nstart ? 4 : int((v >> (2 * (lag - 1 - j))) & 3u);
 }
-
-// softmax(sum_j mat[j, s_j, :]) of a start-free k-mer through the chunk tables; false if the ratio
-// product left the double range (the caller then takes the cooperative path)
-__device__ __forceinline__ bool linear_head_fast(const double* R, uint64_t v, int lag, const ChunkKeys& ck, int nch, double (&f)[A1]) {
-    double p0 = 1.0, p1 = 1.0, p2 = 1.0, p3 = 1.0;
-    int sh = 2 * lag;                           // chunks run from the most significant symbols down
-    for (int ch = 0; ch < nch; ++ch) {
-        const int bits = 2 * (ck.base + (ch < ck.extra ? 1 : 0));
-        sh -= bits;
-        const int q = int(uint32_t(v >> sh) & ((1u << bits) - 1u));
-        const double2 a = *reinterpret_cast<const double2*>(R + (ch * COMBOS + q) * 4);
-        const double2 b = *reinterpret_cast<const double2*>(R + (ch * COMBOS + q) * 4 + 2);
-        p0 *= a.x;
-        p1 *= a.y;
-        p2 *= b.x;
-        p3 *= b.y;
-    }
-    const double z = 1.0 + ((p0 + p1) + (p2 + p3));
-    if (!(z < 1e300)) return false;
-    const double zi = 1.0 / z;
-    f[0] = p0 * zi;
-    f[1] = p1 * zi;
-    f[2] = p2 * zi;
-    f[3] = p3 * zi;
-    f[4] = zi;
-    return true;
-}
-
-// Linear head for one warp tile.  Lanes whose k-mer has start symbols (or whose table product
-// overflowed) are served cooperatively: the warp walks them one at a time, lane j < lag fetches the
-// weight row of position j, and a butterfly sum gives every lane the logits.  Must be called by all 32
-// lanes.  Returns true for lanes that took the chunk-table path (their gradient can be staged by key).
-__device__ __forceinline__ bool linear_head_tile(const double* R, const double* smat, uint64_t code, bool live,
-                                                 int lag, int nch, const ChunkKeys& ck, double (&f)[A1]) {
-    const int lane = threadIdx.x & 31;
-    bool fast = false;
-#pragma unroll
-    for (int b = 0; b < A1; ++b) f[b] = 0.2;
-    if (live && (code >> 58) == 0) fast = linear_head_fast(R, code & PAYLOAD_MASK, lag, ck, nch, f);
-    unsigned todo = __ballot_sync(0xffffffffu, live && !fast);
-    while (todo) {
-        const int src = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const uint64_t cs = __shfl_sync(0xffffffffu, code, src);
-        double l[A1] = {0, 0, 0, 0, 0};
-        if (lane < lag) {
-            const double* row = smat + (lane * A1 + symbol_at(cs & PAYLOAD_MASK, lane, lag, int(cs >> 58))) * A1;
-#pragma unroll
-            for (int b = 0; b < A1; ++b) l[b] = row[b];
-        }
-#pragma unroll
-        for (int b = 0; b < A1; ++b) l[b] = warp_sum(l[b]);
-        if (lane == src) {
-            double m = l[0];
-#pragma unroll
-            for (int b = 1; b < A1; ++b) m = fmax(m, l[b]);
-            double z = 0.0;
-#pragma unroll
-            for (int b = 0; b < A1; ++b) {
-                f[b] = exp(l[b] - m);
-                z += f[b];
-            }
-            const double zi = 1.0 / z;
-#pragma unroll
-            for (int b = 0; b < A1; ++b) f[b] *= zi;
-        }
-    }
-    return fast;
-}
-
 
 __device__ __forceinline__ double pick5(const uint32_t (&c)[A1], int idx) {
     const uint32_t v = idx == 0 ? c[0] : idx == 1 ? c[1] : idx == 2 ? c[2] : idx == 3 ? c[3] : c[4];
@@ -239,282 +132,6 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partials, int 
     double s = 0.0;
     for (int b = 0; b < nblk; ++b) s += partials[int64_t(b) * P + p];
     out[p] += mult * s;
-}
-
-// ------------------------------------------------------------------------------------------------
-// linear head, fused forward + backward
-// ------------------------------------------------------------------------------------------------
-// Per iteration a CTA handles NW tiles of 32 rows.  Phase A: every warp computes one tile (one row per
-// lane) and stages (k-mer payload, g_0..g_3) -- the gradient w.r.t. the logits -- in shared memory.
-// Phase B: warp ch owns gradient chunk table G[ch] (<= 4 positions, 256 keys); it walks the NW staged tiles;
-// a tag array picks one row per key for a plain read-modify-write, rows that lost (key collisions inside the
-// tile: rare for shuffled tables, the rule for the leading chunks of sorted ones) are combined per key
-// (match.any, butterfly sum when they all share one key) and applied by one lane per key.  No atomics.
-template <bool TRAIN_AR>
-__global__ void __launch_bounds__(THREADS, 2)
-linear_train_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ col, int64_t stride,
-                    int64_t n, int lag, const ChunkKeys ck, const double* __restrict__ mat,
-                    const double* __restrict__ h_signed, double* __restrict__ ll_out, double* __restrict__ partials) {
-    extern __shared__ __align__(16) double smem[];
-    const int nch = num_chunks(lag);
-    const int nchg = nch;
-    double* R = smem;                              // [nch][256][4] forward ratio tables
-    double* G = R + nch * COMBOS * 4;              // [nchg][256][4] d ll / d chunk-logits (letters 0..3)
-    double* smat = G + nchg * COMBOS * 4;         // [lag][5][5]
-    double* gmat = smat + lag * A1 * A1;           // [lag][5][5]  gradient from slow-path rows (rare)
-    double* tab_lg = gmat + lag * A1 * A1;         // [TABN] lgamma(S0 + N) - lgamma(S0)
-    double* tab_dg = tab_lg + TABN;                // [TABN] digamma difference
-    double* red = tab_dg + TABN;                   // [32]
-    double* stir = red + 32;                       // [(SMALLC+1)^2] Stirling triangle
-    double* stage_g = stir + STIR_N;               // [NW][4][32]
-    uint64_t* stage_k = reinterpret_cast<uint64_t*>(stage_g + NW * 4 * 32);   // [NW][32]
-    uint64_t* slow_k = stage_k + NW * 32;                                      // [NW][SLOWCAP] start-padded rows
-    double* slow_g = reinterpret_cast<double*>(slow_k + NW * SLOWCAP);         // [NW][SLOWCAP][5]
-    int* slow_n = reinterpret_cast<int*>(slow_g + NW * SLOWCAP * A1);          // [NW]
-    uint8_t* tags = reinterpret_cast<uint8_t*>(slow_n + NW);                   // [nchg][256] scatter tie-break
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const double hinv = exp(-h_signed[0]);         // 1 / h,  h = exp(h_signed)  (bear_net.py:186)
-    for (int i = threadIdx.x; i < lag * A1 * A1; i += blockDim.x) {
-        smat[i] = mat[i];
-        gmat[i] = 0.0;
-    }
-    for (int i = threadIdx.x; i < nchg * COMBOS * 4; i += blockDim.x) G[i] = 0.0;
-    for (int i = threadIdx.x; i < STIR_N; i += blockDim.x) stir[i] = kStirling[i];
-    if (!TRAIN_AR && threadIdx.x < TABN) {
-        // the concentrations of a row sum to 1/h + 5 eps whatever its k-mer (softmax sums to 1)
-        const LgDg t = lgdg_diff<true>(hinv + A1 * BEAR_EPS, double(threadIdx.x));
-        tab_lg[threadIdx.x] = t.add + (t.mul == 1.0 ? 0.0 : log(t.mul));
-        tab_dg[threadIdx.x] = t.dg;
-    }
-    __syncthreads();
-    build_ratio_tables(smat, R, lag);
-    __syncthreads();
-
-    double acc_add = 0.0, dh_sum = 0.0;
-    LogProdLong acc_prod;
-    const int64_t ntiles = (n + 31) >> 5;
-
-    for (int64_t tile0 = int64_t(blockIdx.x) * NW; tile0 < ntiles; tile0 += int64_t(gridDim.x) * NW) {
-        // ---------------- phase A: one row per lane ----------------
-        const int64_t i = ((tile0 + warp) << 5) + lane;
-        const bool in_range = i < n;
-        const uint64_t code = in_range ? __ldg(kmers + i) : 0ull;
-        const Counts r = load_counts(col, stride, i, in_range);
-        const bool live = r.cmax != 0;             // zero-count row: ll = 0 and every gradient is 0
-        const uint32_t steps = warp_steps(live, r.cmax);
-        double f[A1], g[A1] = {0, 0, 0, 0, 0};
-        const bool fast = linear_head_tile(R, smat, code, live, lag, nch, ck, f);
-        double ll_row = 0.0;
-        {
-            double add, prod, w[A1];
-            if (TRAIN_AR) {
-                double p[A1], ri[A1];
-#pragma unroll
-                for (int b = 0; b < A1; ++b) p[b] = f[b] + BEAR_EPS;                 // bear_net.py:68
-                mn_term(p, r, add, prod);
-                inv5(p, ri);
-                double u = 0.0;
-#pragma unroll
-                for (int b = 0; b < A1; ++b) {
-                    w[b] = double(r.c[b]) * ri[b];                                   // d ll / d f_b
-                    u = fma(f[b], w[b], u);
-                }
-#pragma unroll
-                for (int b = 0; b < A1; ++b) g[b] = f[b] * (w[b] - u);
-            } else {
-                double conc[A1];
-#pragma unroll
-                for (int b = 0; b < A1; ++b) conc[b] = fma(f[b], hinv, BEAR_EPS);       // bear_net.py:43
-                letters_term<true>(stir, conc, r, steps, add, prod, w);
-                double tadd, tdg;
-                if (r.n < double(TABN)) {
-                    tadd = tab_lg[int(r.n)];
-                    tdg = tab_dg[int(r.n)];
-                } else {
-                    double tprod;
-                    const double s = ((conc[0] + conc[1]) + (conc[2] + conc[3])) + conc[4];
-                    total_term<true>(s, r, tadd, tprod, tdg);
-                    tadd += log(tprod);
-                }
-                add -= tadd;
-                // d ll/d conc_b = w_b - tdg; d ll/d f_b = that / h; softmax backward:
-                // g_b = f_b (d ll/d f_b - sum_j f_j d ll/d f_j) = f_b (w_b - W) / h,  W = sum_j f_j w_j
-                double W = 0.0;
-#pragma unroll
-                for (int b = 0; b < A1; ++b) W = fma(f[b], w[b], W);
-                if (live) dh_sum -= (W - tdg) * hinv;       // d ll / d h_signed = -sum_b f_b d ll/d f_b
-#pragma unroll
-                for (int b = 0; b < A1; ++b) g[b] = f[b] * hinv * (w[b] - W);
-            }
-            if (live) {
-                if (ll_out) {
-                    ll_row = add + log(prod);
-                    acc_add += ll_row;
-                } else {
-                    acc_add += add;
-                    acc_prod.push(0.0, prod);
-                }
-            }
-        }
-        if (ll_out && in_range) ll_out[i] = ll_row;
-        const uint64_t key = (live && fast) ? (code & PAYLOAD_MASK) : KEY_INVALID;
-        // start-padded k-mers (rare): staged separately, up to SLOWCAP per tile; one warp owns the
-        // per-position table gmat in phase B.  Overflow rows are scattered right here with atomics,
-        // lane j handling position j.
-        const bool slow = live && !fast;
-        unsigned todo = __ballot_sync(0xffffffffu, slow);
-        if (lane == 0) slow_n[warp] = min(__popc(todo), SLOWCAP);
-        if (todo) {
-            const int rank = __popc(todo & ((1u << lane) - 1u));
-            if (slow && rank < SLOWCAP) {
-                slow_k[warp * SLOWCAP + rank] = code;
-#pragma unroll
-                for (int b = 0; b < A1; ++b) slow_g[(warp * SLOWCAP + rank) * A1 + b] = g[b];
-            }
-            todo = __ballot_sync(0xffffffffu, slow && rank >= SLOWCAP);
-            while (todo) {
-                const int src = __ffs(todo) - 1;
-                todo &= todo - 1;
-                const uint64_t cs = __shfl_sync(0xffffffffu, code, src);
-                double gs[A1];
-#pragma unroll
-                for (int b = 0; b < A1; ++b) gs[b] = __shfl_sync(0xffffffffu, g[b], src);
-                if (lane < lag) {
-                    double* dst = gmat + (lane * A1 + symbol_at(cs & PAYLOAD_MASK, lane, lag, int(cs >> 58))) * A1;
-#pragma unroll
-                    for (int b = 0; b < A1; ++b) atomicAdd(dst + b, gs[b]);
-                }
-            }
-        }
-        stage_k[warp * 32 + lane] = key;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) stage_g[(warp * 4 + b) * 32 + lane] = g[b];
-        __syncthreads();
-        // ---------------- phase B: warp ch scatters chunk ch of every staged tile ----------------
-        for (int ch = warp; ch < nchg; ch += NW) {
-            double* Gc = G + ch * COMBOS * 4;
-            uint8_t* tg = tags + ch * COMBOS;
-            const uint32_t kmask = chunk_mask(ch, ck);
-            const int kshift = chunk_shift(lag, ch, ck);
-            for (int t = 0; t < NW; ++t) {
-                const uint64_t k = stage_k[t * 32 + lane];
-                bool pending = k != KEY_INVALID;
-                if (!__any_sync(0xffffffffu, pending)) continue;
-                const int q = pending ? int(uint32_t(k >> kshift) & kmask) : 0x7fffffff;
-                const double* sg = stage_g + t * 4 * 32;
-                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-                if (pending) {
-                    s0 = sg[lane];
-                    s1 = sg[32 + lane];
-                    s2 = sg[64 + lane];
-                    s3 = sg[96 + lane];
-                }
-                // Rows of a tile with equal keys collide on one table entry.  Two tag rounds: every pending lane
-                // writes its id into tags[q]; whoever reads its own id back owns q and does a plain
-                // read-modify-write.  With 256 random keys that settles all but a few percent of the tiles.
-                unsigned left = 0;
-#pragma unroll
-                for (int round = 0; round < 2; ++round) {
-                    if (pending) tg[q] = uint8_t(lane);
-                    __syncwarp();
-                    if (pending && tg[q] == uint8_t(lane)) {
-                        double2* dst = reinterpret_cast<double2*>(Gc + q * 4);
-                        double2 a = dst[0], b2 = dst[1];
-                        a.x += s0;
-                        a.y += s1;
-                        b2.x += s2;
-                        b2.y += s3;
-                        dst[0] = a;
-                        dst[1] = b2;
-                        pending = false;
-                    }
-                    left = __ballot_sync(0xffffffffu, pending);
-                    if (left == 0) break;
-                }
-                if (left == 0) continue;
-                // Leftovers (always few for random keys; nearly the whole tile for the leading chunks of a
-                // sorted table or a chunk with few keys): combine equal keys, then one lane per key updates.
-                const unsigned grp = __match_any_sync(0xffffffffu, pending ? q : 0x7fffffff);
-                const bool leader = pending && (__ffs(grp) - 1) == lane;
-                if (__all_sync(0xffffffffu, !pending || grp == left)) {
-                    if (!pending) s0 = s1 = s2 = s3 = 0.0;
-                    s0 = warp_sum(s0);                 // one key for all leftovers: butterfly sum
-                    s1 = warp_sum(s1);
-                    s2 = warp_sum(s2);
-                    s3 = warp_sum(s3);
-                } else if (leader) {
-                    unsigned rest = grp & (grp - 1);
-                    while (rest) {
-                        const int j = __ffs(rest) - 1;
-                        rest &= rest - 1;
-                        s0 += sg[j];
-                        s1 += sg[32 + j];
-                        s2 += sg[64 + j];
-                        s3 += sg[96 + j];
-                    }
-                }
-                if (leader) {
-                    double2* dst = reinterpret_cast<double2*>(Gc + q * 4);
-                    double2 a = dst[0], b2 = dst[1];
-                    a.x += s0;
-                    a.y += s1;
-                    b2.x += s2;
-                    b2.y += s3;
-                    dst[0] = a;
-                    dst[1] = b2;
-                }
-                __syncwarp();
-            }
-        }
-        if (warp == (nchg < NW ? nchg : 0)) {       // owner of gmat: the first warp without a chunk table
-            for (int t = 0; t < NW; ++t) {
-                const int cnt = slow_n[t];
-                for (int k = 0; k < cnt; ++k) {
-                    const uint64_t cs = slow_k[t * SLOWCAP + k];
-                    if (lane < lag) {
-                        double* dst = gmat + (lane * A1 + symbol_at(cs & PAYLOAD_MASK, lane, lag, int(cs >> 58))) * A1;
-                        const double* gs = slow_g + (t * SLOWCAP + k) * A1;
-#pragma unroll
-                        for (int b = 0; b < A1; ++b) dst[b] += gs[b];
-                    }
-                }
-            }
-        }
-        __syncthreads();
-    }
-
-    const int P = 2 + lag * A1 * A1;
-    double* out = partials + int64_t(blockIdx.x) * P;
-    const double ll_thread = acc_add + acc_prod.value();
-    const double ll_blk = block_sum(ll_thread, red);
-    const double dh_blk = block_sum(dh_sum, red);
-    if (threadIdx.x == 0) {
-        out[0] = ll_blk;
-        out[1] = dh_blk;
-    }
-    __syncthreads();
-    // marginalise the chunk-table gradients back onto mat[j, s, b]
-    for (int idx = threadIdx.x; idx < lag * A1 * A1; idx += blockDim.x) {
-        const int b = idx % A1, s = (idx / A1) % A1, j = idx / (A1 * A1);
-        double val = gmat[idx];
-        if (s < 4) {
-            int ch = 0;
-            ChunkGeom cg = chunk_geom(lag, nchg, 0);
-            while (j >= cg.start + cg.size) cg = chunk_geom(lag, nchg, ++ch);
-            const int p = j - cg.start, r = cg.size;
-            const int shift = 2 * (r - 1 - p);
-            double acc = 0.0;
-            for (int q = 0; q < (1 << (2 * r)); ++q) {
-                if (((q >> shift) & 3) != s) continue;
-                const double* src = G + (ch * COMBOS + q) * 4;
-                if (b < 4) acc += src[b];
-                else acc -= (src[0] + src[1]) + (src[2] + src[3]);   // the 5 logit gradients sum to 0
-            }
-            val += acc;
-        }
-        out[2 + idx] = val;
-    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -629,6 +246,67 @@ __device__ __noinline__ void linear_head_exact(const double* __restrict__ mat, u
     for (int b = 0; b < A1; ++b) f[b] /= z;
 }
 
+// Extended, swizzled ratio tables R[nch][ENT][4] of the linear head and the symbol table they are built from.
+// Needs a __syncthreads() by the caller afterwards.
+__device__ void build_ext_tables(const double* __restrict__ mat, double* R, uint16_t* symtab, int lag, const ChunkKeys& ck) {
+    const int nch = num_chunks(lag);
+    for (int i = threadIdx.x; i < 2 * ENT; i += blockDim.x) {
+        const int r = ck.base + (i < ENT ? 1 : 0);           // size class 0: base + 1 positions, class 1: base
+        symtab[i] = (r >= 1 && r <= CHUNK) ? ext_symbols(i % ENT, r) : uint16_t(0xffff);
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < nch * ENT; idx += blockDim.x) {
+        const int ch = idx / ENT, e = idx - ch * ENT;
+        const ChunkGeom cg = chunk_geom(lag, nch, ch);
+        const uint32_t syms = symtab[(ch < ck.extra ? 0 : ENT) + e];
+        double l[A1] = {0, 0, 0, 0, 0};
+        if (syms != 0xffffu) {
+            for (int p = 0; p < cg.size; ++p) {
+                const double* row = mat + ((cg.start + p) * A1 + int((syms >> (3 * p)) & 7u)) * A1;
+#pragma unroll
+                for (int b = 0; b < A1; ++b) l[b] += __ldg(row + b);
+            }
+        }
+        const int sw = half_swizzle(e);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) R[idx * 4 + ((b & 2) ^ sw) + (b & 1)] = exp(l[b] - l[4]);
+    }
+}
+
+// softmax(sum_j mat[j, s_j, :]) of one k-mer as the normalised product of its chunk-table rows
+__device__ __forceinline__ void linear_head_ext(const double* R, const double* __restrict__ mat, uint64_t code, int lag,
+                                                const ChunkKeys& ck, int nch, double (&f)[A1]) {
+    const int ns = int(code >> 58);
+    const uint64_t v = code & PAYLOAD_MASK;
+    double p0 = 1.0, p1 = 1.0, p2 = 1.0, p3 = 1.0;
+    int sh = 2 * lag, c0 = 0;
+    for (int ch = 0; ch < nch; ++ch) {
+        const int rr = ck.base + (ch < ck.extra ? 1 : 0);
+        sh -= 2 * rr;
+        int q = int(uint32_t(v >> sh) & ((1u << (2 * rr)) - 1u));
+        if (ns > c0) q = ext_key(uint32_t(q), rr, ns - c0);
+        c0 += rr;
+        const int sw = half_swizzle(q);
+        const double2 a = *reinterpret_cast<const double2*>(R + (ch * ENT + q) * 4 + sw);
+        const double2 b = *reinterpret_cast<const double2*>(R + (ch * ENT + q) * 4 + (sw ^ 2));
+        p0 *= a.x;
+        p1 *= a.y;
+        p2 *= b.x;
+        p3 *= b.y;
+    }
+    const double z = 1.0 + ((p0 + p1) + (p2 + p3));
+    if (z < 1e300 && z > 1e-300) {
+        const double zi = 1.0 / z;
+        f[0] = p0 * zi;
+        f[1] = p1 * zi;
+        f[2] = p2 * zi;
+        f[3] = p3 * zi;
+        f[4] = zi;
+    } else {
+        linear_head_exact(mat, code, lag, f);
+    }
+}
+
 struct RowIn {
     uint64_t code;
     uint32_t c[A1];
@@ -669,10 +347,6 @@ linear_train2_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restr
     const double hinv = exp(-h_signed[0]);                  // 1 / h,  h = exp(h_signed)  (bear_net.py:186)
 
     // ---------------- tables ----------------
-    for (int i = threadIdx.x; i < 2 * ENT; i += blockDim.x) {
-        const int r = ck.base + (i < ENT ? 1 : 0);           // size class 0: base + 1 positions, class 1: base
-        symtab[i] = (r >= 1 && r <= CHUNK) ? ext_symbols(i % ENT, r) : uint16_t(0xffff);
-    }
     for (int i = threadIdx.x; i < nch * ENT * 4; i += blockDim.x) G[i] = 0.0;
     for (int i = threadIdx.x; i < STIR_N; i += blockDim.x) stir[i] = kStirling[i];
     for (int i = threadIdx.x; i < 2 * tiles; i += blockDim.x) stage_m[i] = 0u;
@@ -682,23 +356,7 @@ linear_train2_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restr
         tab_lg[threadIdx.x] = t.add + (t.mul == 1.0 ? 0.0 : log(t.mul));
         tab_dg[threadIdx.x] = t.dg;
     }
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < nch * ENT; idx += blockDim.x) {
-        const int ch = idx / ENT, e = idx - ch * ENT;
-        const ChunkGeom cg = chunk_geom(lag, nch, ch);
-        const uint32_t syms = symtab[(ch < ck.extra ? 0 : ENT) + e];
-        double l[A1] = {0, 0, 0, 0, 0};
-        if (syms != 0xffffu) {
-            for (int p = 0; p < cg.size; ++p) {
-                const double* row = mat + ((cg.start + p) * A1 + int((syms >> (3 * p)) & 7u)) * A1;
-#pragma unroll
-                for (int b = 0; b < A1; ++b) l[b] += __ldg(row + b);
-            }
-        }
-        const int sw = half_swizzle(e);
-#pragma unroll
-        for (int b = 0; b < 4; ++b) R[idx * 4 + ((b & 2) ^ sw) + (b & 1)] = exp(l[b] - l[4]);
-    }
+    build_ext_tables(mat, R, symtab, lag, ck);
     __syncthreads();
 
     double acc_add = 0.0, dh_sum = 0.0;
@@ -1018,20 +676,16 @@ eval_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ tes
     // the sum of a row's BEAR concentrations is row-independent when there is no conditioning column
     // and the head is normalised (or absent)
     constexpr bool TOT_TAB = !HAS_TRAIN && HEAD != BEAR_HEAD_EXPLICIT;
-    double* R = smem;
-    double* smat = R + (LIN ? nch * COMBOS * 4 : 0);
-    double* red = smat + (LIN ? lag * A1 * A1 : 0);
+    double* R = smem;                                               // [nch][ENT][4] extended ratio tables
+    uint16_t* symtab = reinterpret_cast<uint16_t*>(R + (LIN ? nch * ENT * 4 : 0));
+    double* red = R + (LIN ? nch * ENT * 4 + (2 * ENT * 2) / 8 : 0);
     constexpr int NM = NH > NV ? NH : NV;
     double* tab_ear = red + 32;                    // [NM][TABN]  lgamma(S0_k + N) - lgamma(S0_k)
     double* tab_van = tab_ear + NM * TABN;         // [NM][TABN]  lgamma(van_k + eps + c) - lgamma(van_k + eps)
     double* tab_vtot = tab_van + NM * TABN;        // [NM][TABN]  lgamma(5 (van_k + eps) + N) - lgamma(5 (van_k + eps))
     double* stir = tab_vtot + NM * TABN;           // Stirling triangle
     for (int i = threadIdx.x; i < STIR_N; i += blockDim.x) stir[i] = kStirling[i];
-    if (LIN) {
-        for (int i = threadIdx.x; i < lag * A1 * A1; i += blockDim.x) smat[i] = head[i];
-        __syncthreads();
-        build_ratio_tables(smat, R, lag);
-    }
+    if (LIN) build_ext_tables(head, R, symtab, lag, ck);
     double hinv[NH], van[NV];
 #pragma unroll
     for (int k = 0; k < NH; ++k) hinv[k] = k < H ? 1.0 / d_h[k] : 1.0;
@@ -1075,7 +729,9 @@ eval_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ tes
         }
         double f[A1];
         if (LIN) {
-            linear_head_tile(R, smat, in_range ? __ldg(kmers + i) : 0ull, live, lag, nch, ck, f);
+#pragma unroll
+            for (int b = 0; b < A1; ++b) f[b] = 0.2;
+            if (live) linear_head_ext(R, head, __ldg(kmers + i), lag, ck, nch, f);
         } else {
 #pragma unroll
             for (int b = 0; b < A1; ++b)
@@ -1086,6 +742,7 @@ eval_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ tes
         const uint64_t grow = uint64_t(row0 + i);
         const bool use_tab = !HAS_TRAIN && r.n < double(TABN);
         double dummy[A1];
+        uint64_t van_hash = 0;
         // BEAR: conc = f / h + train + eps   (bear_net.py:43, 335-337)
 #pragma unroll
         for (int k = 0; k < NH; ++k) {
@@ -1149,8 +806,17 @@ eval_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ tes
                     if (live) van_add[k] += (add - tadd) + log(prod / tprod);
                 }
                 if (live) {
-                    const int best = HAS_TRAIN ? noisy_argmax5(conc, 100.0 * BEAR_EPS, seed, grow, 200 + uint64_t(k))
-                                               : (seed < 0 ? 0 : int(tie_hash(seed, grow, 200 + uint64_t(k)) % uint32_t(A1)));
+                    // no conditioning column: the five concentrations are equal and the noisy argmax is a uniform
+                    // pick; one hash per row serves up to four priors (16-bit fields, multiply-shift to 0..4)
+                    int best;
+                    if (HAS_TRAIN) {
+                        best = noisy_argmax5(conc, 100.0 * BEAR_EPS, seed, grow, 200 + uint64_t(k));
+                    } else if (seed < 0) {
+                        best = 0;
+                    } else {
+                        if ((k & 3) == 0) van_hash = mix64(uint64_t(seed) ^ (grow * 0x9E3779B97F4A7C15ull) ^ (uint64_t(200 + k) * 0xD1B54A32D192ED03ull));
+                        best = int((uint32_t(van_hash >> (16 * (k & 3))) & 0xffffu) * 5u >> 16);
+                    }
                     cor_van[k] += pick5(r.c, best);
                 }
             }
@@ -1292,16 +958,10 @@ int grid_for(int64_t n, int cap = MAX_GRID) {
     return int(blocks < cap ? blocks : cap);
 }
 
-size_t train_smem_bytes(int lag) {
-    return sizeof(double) * (size_t(num_chunks(lag)) * COMBOS * 4 + size_t(num_chunks(lag)) * COMBOS * 4 +
-                             size_t(lag) * A1 * A1 * 2 + 2 * TABN + 32 + STIR_N + NW * 4 * 32 + NW * 32 +
-                             NW * SLOWCAP * (1 + A1)) +
-           sizeof(int) * NW + size_t(num_chunks(lag)) * COMBOS;
-}
 
 size_t eval_smem_bytes(int head, int lag, int nm) {
     size_t d = 32 + size_t(3) * nm * TABN + STIR_N;
-    if (head == BEAR_HEAD_LINEAR) d += size_t(num_chunks(lag)) * COMBOS * 4 + size_t(lag) * A1 * A1;
+    if (head == BEAR_HEAD_LINEAR) d += size_t(num_chunks(lag)) * ENT * 4 + (2 * ENT * 2) / 8;
     return sizeof(double) * d;
 }
 
@@ -1363,41 +1023,23 @@ extern "C" int bear_linear_train_step(const uint64_t* d_kmers, const uint32_t* d
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int P = 2 + lag * A1 * A1;
     const ChunkKeys ck = make_chunk_keys(lag);
-    static const bool use_v1 = getenv("BEAR_TRAIN_V1") != nullptr;
-    if (!use_v1) {
-        const int nch = num_chunks(lag);
-        const int tpw = size_t(train2_layout(nch, 2).total) <= size_t(227 * 1024) ? 2 : 1;
-        const size_t smem2 = size_t(train2_layout(nch, tpw).total);
-        const int64_t ntiles = (n + 31) / 32, per_cta = int64_t(T2_NW - nch) * tpw;
-        const int64_t want = (ntiles + per_cta - 1) / per_cta;
-        const int grid2 = int(want < 148 ? want : 148);
-        if (train_ar) {
-            if (set_smem(linear_train2_kernel<true>, smem2)) return BEAR_ERR_CUDA;
-            linear_train2_kernel<true><<<grid2, T2_THREADS, smem2, st>>>(d_kmers + row0, d_col + row0, stride, n, lag, ck, tpw,
-                                                                        d_mat, d_h_signed, d_ll_out, d_workspace);
-        } else {
-            if (set_smem(linear_train2_kernel<false>, smem2)) return BEAR_ERR_CUDA;
-            linear_train2_kernel<false><<<grid2, T2_THREADS, smem2, st>>>(d_kmers + row0, d_col + row0, stride, n, lag, ck, tpw,
-                                                                         d_mat, d_h_signed, d_ll_out, d_workspace);
-        }
-        BEAR_LAUNCH_CHECK("linear_train2_kernel");
-        reduce_partials_kernel<<<(P + 127) / 128, 128, 0, st>>>(d_workspace, grid2, P, -scale, d_flat);
-        BEAR_LAUNCH_CHECK("reduce_partials_kernel");
-        return BEAR_OK;
-    }
-    const int grid = grid_for(n, 148 * 2);
-    const size_t smem = train_smem_bytes(lag);
+    const int nch = num_chunks(lag);
+    const int tpw = size_t(train2_layout(nch, 2).total) <= size_t(227 * 1024) ? 2 : 1;
+    const size_t smem2 = size_t(train2_layout(nch, tpw).total);
+    const int64_t ntiles = (n + 31) / 32, per_cta = int64_t(T2_NW - nch) * tpw;
+    const int64_t want = (ntiles + per_cta - 1) / per_cta;
+    const int grid2 = int(want < 148 ? want : 148);
     if (train_ar) {
-        if (set_smem(linear_train_kernel<true>, smem)) return BEAR_ERR_CUDA;
-        linear_train_kernel<true><<<grid, THREADS, smem, st>>>(d_kmers + row0, d_col + row0, stride, n, lag, ck, d_mat,
-                                                              d_h_signed, d_ll_out, d_workspace);
+        if (set_smem(linear_train2_kernel<true>, smem2)) return BEAR_ERR_CUDA;
+        linear_train2_kernel<true><<<grid2, T2_THREADS, smem2, st>>>(d_kmers + row0, d_col + row0, stride, n, lag, ck, tpw,
+                                                                    d_mat, d_h_signed, d_ll_out, d_workspace);
     } else {
-        if (set_smem(linear_train_kernel<false>, smem)) return BEAR_ERR_CUDA;
-        linear_train_kernel<false><<<grid, THREADS, smem, st>>>(d_kmers + row0, d_col + row0, stride, n, lag, ck, d_mat,
-                                                               d_h_signed, d_ll_out, d_workspace);
+        if (set_smem(linear_train2_kernel<false>, smem2)) return BEAR_ERR_CUDA;
+        linear_train2_kernel<false><<<grid2, T2_THREADS, smem2, st>>>(d_kmers + row0, d_col + row0, stride, n, lag, ck, tpw,
+                                                                     d_mat, d_h_signed, d_ll_out, d_workspace);
     }
-    BEAR_LAUNCH_CHECK("linear_train_kernel");
-    reduce_partials_kernel<<<(P + 127) / 128, 128, 0, st>>>(d_workspace, grid, P, -scale, d_flat);
+    BEAR_LAUNCH_CHECK("linear_train2_kernel");
+    reduce_partials_kernel<<<(P + 127) / 128, 128, 0, st>>>(d_workspace, grid2, P, -scale, d_flat);
     BEAR_LAUNCH_CHECK("reduce_partials_kernel");
     return BEAR_OK;
 }
