@@ -34,6 +34,10 @@ constexpr int THREADS = 256;
 constexpr int MAX_GRID = 148 * 4;
 constexpr int TABN = 64;         // counts below TABN index the per-CTA tables of row-independent terms
 constexpr uint64_t PAYLOAD_MASK = (1ull << 58) - 1;
+#ifndef BEAR_EVAL_CTAS
+#define BEAR_EVAL_CTAS 2
+#endif
+#define EVAL_MIN_CTAS(NH, NV) (((NH) <= 1 && (NV) <= 4) ? BEAR_EVAL_CTAS : 2)
 
 __host__ __device__ inline int num_chunks(int lag) { return (lag + CHUNK - 1) / CHUNK; }
 
@@ -316,7 +320,7 @@ __device__ __forceinline__ RowIn load_row(const uint64_t* __restrict__ kmers, co
                                           int64_t stride, int64_t i, int64_t n) {
     RowIn r;
     const bool ok = i < n;
-    r.code = ok ? __ldg(kmers + i) : 0ull;
+    r.code = (ok && kmers) ? __ldg(kmers + i) : 0ull;
 #pragma unroll
     for (int b = 0; b < A1; ++b) r.c[b] = ok ? __ldg(col + b * stride + i) : 0u;
     return r;
@@ -665,7 +669,7 @@ explicit_train_kernel(const uint32_t* __restrict__ col, int64_t stride, int64_t 
 // ------------------------------------------------------------------------------------------------
 // NH / NV bound the number of h values (H) and of BMM priors (V) of one launch.
 template <int HEAD, int NH, int NV, bool HAS_TRAIN>
-__global__ void __launch_bounds__(THREADS, (NH <= 1 && NV <= 4) ? 3 : 2)
+__global__ void __launch_bounds__(THREADS, EVAL_MIN_CTAS(NH, NV))
 eval_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ test_col,
             const uint32_t* __restrict__ train_col, int64_t stride, int64_t row0, int64_t n, int lag,
             const ChunkKeys ck, const double* __restrict__ head, const double* __restrict__ d_h, int H,
@@ -716,22 +720,47 @@ eval_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ tes
     double arm_add = 0.0, cor_arm = 0.0, total = 0.0;
     LogProdLong arm_prod;
 
-    for (int64_t base = int64_t(blockIdx.x) * blockDim.x; base < n; base += int64_t(gridDim.x) * blockDim.x) {
+    // the k-mer and test counts of the next row are fetched while the current row is evaluated
+    const int64_t gstep = int64_t(gridDim.x) * blockDim.x;
+    RowIn nxt = load_row(LIN ? kmers : nullptr, test_col, stride, int64_t(blockIdx.x) * blockDim.x + threadIdx.x, n);
+    uint32_t tnx[A1] = {0, 0, 0, 0, 0};
+    if (HAS_TRAIN) {
+        const int64_t i0 = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+#pragma unroll
+        for (int b = 0; b < A1; ++b) tnx[b] = i0 < n ? __ldg(train_col + b * stride + i0) : 0u;
+    }
+    for (int64_t base = int64_t(blockIdx.x) * blockDim.x; base < n; base += gstep) {
         const int64_t i = base + threadIdx.x;
         const bool in_range = i < n;
-        const Counts r = load_counts(test_col, stride, i, in_range);
+        const RowIn cur = nxt;
+        nxt = load_row(LIN ? kmers : nullptr, test_col, stride, i + gstep, n);
+        uint32_t tc[A1] = {0, 0, 0, 0, 0};
+        if (HAS_TRAIN) {
+#pragma unroll
+            for (int b = 0; b < A1; ++b) tc[b] = tnx[b];
+#pragma unroll
+            for (int b = 0; b < A1; ++b) tnx[b] = i + gstep < n ? __ldg(train_col + b * stride + i + gstep) : 0u;
+        }
+        Counts r;
+#pragma unroll
+        for (int b = 0; b < A1; ++b) r.c[b] = cur.c[b];
+        r.cmax = max(max(max(r.c[0], r.c[1]), max(r.c[2], r.c[3])), r.c[4]);
+        if (r.cmax < (1u << 29))
+            r.n = double((r.c[0] + r.c[1]) + (r.c[2] + r.c[3]) + r.c[4]);
+        else
+            r.n = (double(r.c[0]) + double(r.c[1])) + (double(r.c[2]) + double(r.c[3])) + double(r.c[4]);
         const bool live = r.cmax != 0;             // no test transitions: contributes 0 to every output
         const uint32_t steps = warp_steps(live, r.cmax);
         double t[A1] = {0, 0, 0, 0, 0};
         if (HAS_TRAIN && live) {
 #pragma unroll
-            for (int b = 0; b < A1; ++b) t[b] = double(__ldg(train_col + b * stride + i));
+            for (int b = 0; b < A1; ++b) t[b] = double(tc[b]);
         }
         double f[A1];
         if (LIN) {
 #pragma unroll
             for (int b = 0; b < A1; ++b) f[b] = 0.2;
-            if (live) linear_head_ext(R, head, __ldg(kmers + i), lag, ck, nch, f);
+            if (live) linear_head_ext(R, head, cur.code, lag, ck, nch, f);
         } else {
 #pragma unroll
             for (int b = 0; b < A1; ++b)
@@ -1079,7 +1108,7 @@ extern "C" int bear_eval_step(const uint64_t* d_kmers, const uint32_t* d_test_co
     if (n == 0) return BEAR_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool small = H <= 1 && V <= 4;
-    const int grid = grid_for(n, 148 * (small ? 3 : 2));
+    const int grid = grid_for(n, 148 * (small ? BEAR_EVAL_CTAS : 2));
     const size_t smem = eval_smem_bytes(head, lag, small ? 4 : 8);
     const uint64_t* km = d_kmers ? d_kmers + row0 : nullptr;
     const uint32_t* tr = d_train_col ? d_train_col + row0 : nullptr;

@@ -28,9 +28,9 @@ sys.path.insert(0, ROOT)
 LAG = 20
 TRAIN_BYTES_PER_ROW = 28          # 8 B packed k-mer + 5 x 4 B counts (one column)  SURVEY.md 8(d)
 EVAL_BYTES_PER_ROW = 28           # ds_loc_train = -1: k-mer + the test column
-# dram__bytes_read.sum + dram__bytes_write.sum of linear_train_kernel per row, from the ncu --set full capture
-# profiles/r1_final_train_raw.csv (7.519 GB + 0.008 GB over 268 435 456 rows)
-TRAIN_DRAM_BYTES_PER_ROW_NCU = 28.04
+# dram__bytes_read.sum + dram__bytes_write.sum of linear_train2_kernel per row, from the ncu --set full capture
+# profiles/r1_train2_raw.csv (1.880 GB + 0.006 GB over 67 108 864 rows)
+TRAIN_DRAM_BYTES_PER_ROW_NCU = 28.10
 DEFAULT_ROWS = 1 << 31
 
 
@@ -294,12 +294,14 @@ def run_ours(args, rank, world_size, local_rank):
     for _ in range(2):
         e2e_step()
     barrier()
-    t0 = time.perf_counter()
     e_steps = max(3, min(args.steps, 10))
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()                       # device clock; every step ends with a stream synchronize (the D2H read)
     for _ in range(e_steps):
         e2e_step()
+    g1.record()
     barrier()
-    e_dt = torch.tensor([(time.perf_counter() - t0) / e_steps], dtype=torch.float64, device=dev)
+    e_dt = torch.tensor([g0.elapsed_time(g1) * 1e-3 / e_steps], dtype=torch.float64, device=dev)
     if world_size > 1:
         dist.all_reduce(e_dt, op=dist.ReduceOp.MAX)
     e2e_value = 2.0 * e_rows * world_size / float(e_dt)
@@ -331,9 +333,9 @@ def run_ours(args, rank, world_size, local_rank):
         'e2e': {'value': e2e_value, 'unit': 'k-mer transition rows/s', 'h2d_bytes_per_step': h2d,
                 'd2h_bytes_per_step': d2h, 'rows_per_gpu_per_step': e_rows},
         'gpu_launches': args.steps * 6,
-        'roofline': {'bound': 'hbm', 'kernel': 'linear_train_kernel<false>', 'achieved': achieved, 'peak': peak,
+        'roofline': {'bound': 'hbm', 'kernel': 'linear_train2_kernel<false>', 'achieved': achieved, 'peak': peak,
                      'unit': 'GB/s', 'frac': achieved / peak, 'traffic': TRAIN_DRAM_BYTES_PER_ROW_NCU * n,
-                     'traffic_note': 'bytes per launch = ncu dram read+write per row (profiles/r1_final_train_raw.csv) x rows',
+                     'traffic_note': 'bytes per launch = ncu dram read+write per row (profiles/r1_train2_raw.csv) x rows',
                      'algorithmic_bytes': TRAIN_BYTES_PER_ROW * n,
                      'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s',
                      'kernel_ms': train_ms, 'bytes_per_row': TRAIN_BYTES_PER_ROW},

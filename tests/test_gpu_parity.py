@@ -209,6 +209,69 @@ def test_linear_train_step_synthetic(cuda, lag, dense):
         _check_train_step(cuda, codes, counts, lag, 1, train_ar, -0.7, seed=lag, num_kmers=123456)
 
 
+@pytest.mark.parametrize('lag', [2, 5, 13, 20])
+def test_linear_train_step_mostly_start_padded(cuda, lag):
+    """Half of the k-mers carry a start-symbol prefix of every possible length: they take the same chunk-table
+    path as plain k-mers (the tables hold the start patterns), including the gradient rows of the start symbol."""
+    codes, counts = synth_table(4000, lag, 1, seed=100 + lag, start_frac=0.5)
+    _check_train_step(cuda, codes, counts, lag, 0, False, 0.4, seed=lag)
+    _check_train_step(cuda, codes, counts, lag, 0, True, 0.4, seed=lag)
+
+
+def test_linear_train_step_many_tiles_per_cta(cuda):
+    """More rows than one pass of the persistent grid (148 CTAs x 22 tiles x 32 rows): every CTA iterates, the
+    double-buffered stage is reused and the last iteration is ragged."""
+    codes, counts = synth_table(148 * 22 * 32 * 2 + 777, 20, 1, seed=5)
+    _check_train_step(cuda, codes, counts, 20, 0, False, -0.2, seed=1)
+
+
+def test_linear_train_step_few_distinct_kmers(cuda):
+    """Tiles in which many rows share chunk keys (a handful of distinct k-mers, repeated and in runs): the ranked
+    read-modify-write rounds and the butterfly path for keys with more than five rows in a tile."""
+    rng = np.random.default_rng(8)
+    base, counts = synth_table(6, 9, 1, seed=2, start_frac=0.3)
+    pick = np.concatenate([rng.integers(0, 6, size=2000), np.repeat(np.arange(6), 40), np.zeros(100, dtype=np.int64)])
+    codes = base[pick]
+    cnt = rng.poisson(2.0, size=(len(codes), 1, 5)).astype(np.int64)
+    _check_train_step(cuda, codes, cnt, 9, 0, False, 0.1, seed=4)
+    _check_train_step(cuda, codes, cnt, 9, 0, True, 0.1, seed=4)
+
+
+def test_linear_head_exact_fallback_on_extreme_logits(cuda):
+    """Logit spreads of several hundred overflow the product of table ratios; the kernels then evaluate the
+    max-subtracted softmax of that row directly.  Train step and evaluation stay finite and match the oracle."""
+    from bear_b200 import _lib, dataloader as dl
+    from bear_b200._lib import lib, check, ptr
+    O = _oracle()
+    lag, K = 20, 600
+    codes, counts = synth_table(K, lag, 1, seed=12, start_frac=0.1)
+    gen = torch.Generator().manual_seed(3)
+    mat = torch.randn(lag, 5, 5, dtype=torch.float64, generator=gen) * 60.0
+    table = dl.KmerTable.from_arrays((codes, lag), counts, 'dna')
+    k, c = table.device_tensors()
+    hs = torch.tensor(0.2, dtype=torch.float64)
+    flat = torch.zeros(2 + mat.numel(), dtype=torch.float64, device=cuda)
+    ll = torch.empty(K, dtype=torch.float64, device=cuda)
+    ws = torch.empty(lib.bear_workspace_doubles(K, lag, mat.numel()), dtype=torch.float64, device=cuda)
+    mat_d, hs_d = mat.to(cuda), hs.to(cuda)
+    check(lib.bear_linear_train_step(ptr(k), table.col_ptr(0), table.stride, 0, K, lag, ptr(mat_d), ptr(hs_d), 1.0, 0,
+                                     ptr(flat), ptr(ll), ptr(ws), _lib.stream()))
+    oh = O.one_hot(dl.decode_kmers(codes, lag, 'dna'))
+    loss, ll_want, grads = O.train_step_grads(oh, torch.tensor(counts[:, 0], dtype=torch.float64), hs, [mat], 'linear', K, False)
+    assert torch.isfinite(flat).all()
+    assert abs(float(flat[0]) - float(loss)) <= 1e-9 * abs(float(loss))
+    assert float((ll.cpu() - ll_want).abs().max()) <= 1e-9 * float(ll_want.abs().max())
+    assert rel_err(flat[2:].cpu().numpy(), grads[1].reshape(-1).numpy()) <= 1e-7
+    acc = torch.zeros(2 + 2 + 2 + 1, dtype=torch.float64, device=cuda)
+    h = torch.tensor([1.5], dtype=torch.float64, device=cuda)
+    van = torch.tensor([1.0], dtype=torch.float64, device=cuda)
+    check(lib.bear_eval_step(ptr(k), table.col_ptr(0), None, table.stride, 0, K, lag, _lib.HEAD_LINEAR, ptr(mat_d), ptr(h), 1,
+                             ptr(van), 1, -1, ptr(acc), ptr(ws), _lib.stream()))
+    want = _oracle_eval(codes, counts, lag, 0, -1, [1.5], [1.0], mat)
+    assert abs(float(acc[0]) - float(want[0][0])) <= 1e-9 * abs(float(want[0][0]))
+    assert abs(float(acc[1]) - float(want[1])) <= 1e-9 * abs(float(want[1]))
+
+
 def test_linear_train_step_edge_rows(cuda):
     """empty batch is a no-op; ragged n (not a multiple of anything); all-zero rows contribute 0."""
     from bear_b200 import _lib, dataloader as dl
