@@ -74,7 +74,7 @@ inline CnnDims make_dims(int lag, int W, int F, int H1) {
 
 // shared-memory carve-up (in doubles); every segment has an even length (16-byte alignment)
 struct Layout {
-    int e0, w1s, y, fil, sc0, in0, small, stir, red, codes, stats, soff, fbuf, dfil, dsc0, din0, smallg, total;
+    int e0, w1s, y, fil, sc0, in0, small, stir, red, codes, stats, soff, fbuf, tbuf, dfil, dsc0, din0, smallg, total;
 };
 constexpr int SMALL_N = 16 + 16 + 8;             // int1[16], scale1[16], int2[8]
 constexpr int SMALLG_N = 16 * A1 + 8 + 16 + 16;  // dW2[16][5], dint2[8], dint1[16], dscale1[16]
@@ -89,12 +89,13 @@ __host__ __device__ inline Layout make_layout(const CnnDims& d, int TB, bool tra
     L.sc0 = o;   o += even(d.PF);
     L.in0 = o;   o += even(d.PF);
     L.small = o; o += SMALL_N;
-    L.stir = o;  o += even(STIR_N);
+    L.stir = o;
     L.red = o;   o += 32;
     L.codes = o; o += TB;
     L.stats = o; o += 2 * TB * d.P;                  // (mean, rstd) of every (row, position)
     L.soff = o;  o += even((TB * d.lag + 3) / 4);        // uint16 [TB][lag]: symbol * F
     L.fbuf = o;  o += train ? TB * A1 : 0;               // f, then d objective / d logits, of the tile's rows
+    L.tbuf = o;  o += train ? (A1 + 1) * TB * 2 : 0;     // per row and term: lgamma difference, digamma difference
     L.dfil = o;  o += train ? NWARP * even(d.nfil) : 0;
     L.dsc0 = o;  o += train ? even(d.PF) : 0;
     L.din0 = o;  o += train ? even(d.PF) : 0;
@@ -164,12 +165,12 @@ cnn_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ col,
     double* sc0 = smem + L.sc0;
     double* in0 = smem + L.in0;
     double* small = smem + L.small;
-    double* stir = smem + L.stir;
     double* red = smem + L.red;
     uint64_t* codes = reinterpret_cast<uint64_t*>(smem + L.codes);
     double2* stats = reinterpret_cast<double2*>(smem + L.stats);
     uint16_t* soff = reinterpret_cast<uint16_t*>(smem + L.soff);
     double* fbuf = smem + L.fbuf;
+    double* tbuf = smem + L.tbuf;
     double* dfil = smem + L.dfil;
     double* dsc0 = smem + L.dsc0;
     double* din0 = smem + L.din0;
@@ -196,7 +197,6 @@ cnn_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ col,
         small[16 + threadIdx.x] = threadIdx.x < d.H1 ? params[d.o_sc1 + threadIdx.x] : 0.0;
         if (threadIdx.x < 8) small[32 + threadIdx.x] = threadIdx.x < A1 ? params[d.o_int2 + threadIdx.x] : 0.0;
     }
-    for (int i = threadIdx.x; i < STIR_N; i += THREADS) stir[i] = kStirling[i];
     if (TRAIN) {
         for (int i = threadIdx.x; i < NWARP * nfil2; i += THREADS) dfil[i] = 0.0;
         for (int i = threadIdx.x; i < d.PF; i += THREADS) {
@@ -263,12 +263,17 @@ cnn_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ col,
         __syncthreads();
 
         // ---------------- 1. conv -> layer norm -> elu ----------------
-        for (int idx = pair0; idx < pair1; ++idx) {
+        // two (position, row) pairs per trip: independent dependency chains (pair ranges start and end on even indices)
+        for (int idx = pair0; idx < pair1; idx += 2) {
             const int p = idx / TB, r = idx % TB;
             if (lane < d.F) {
-                const double2 st = stats[idx];
-                const double xhat = (conv_at(fil, soff + r * d.lag, p, lane, d) - st.x) * st.y;
-                E0[r * d.es + p * d.F + lane] = elu(fma(sc0[p * d.F + lane], xhat, in0[p * d.F + lane]));
+                const double2 st0 = stats[idx], st1 = stats[idx + 1];
+                const double sc = sc0[p * d.F + lane], in = in0[p * d.F + lane];
+                const double x0 = fma(sc, (conv_at(fil, soff + r * d.lag, p, lane, d) - st0.x) * st0.y, in);
+                const double x1 = fma(sc, (conv_at(fil, soff + (r + 1) * d.lag, p, lane, d) - st1.x) * st1.y, in);
+                const double ex0 = exp(fmin(x0, 0.0)), ex1 = exp(fmin(x1, 0.0));     // tf.nn.elu: exp(x) - 1 for x < 0
+                E0[r * d.es + p * d.F + lane] = x0 > 0.0 ? x0 : ex0 - 1.0;
+                E0[(r + 1) * d.es + p * d.F + lane] = x1 > 0.0 ? x1 : ex1 - 1.0;
             }
         }
         __syncthreads();
@@ -334,7 +339,33 @@ cnn_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ col,
         __syncthreads();
         if (MODE == MODE_FWD) continue;
 
-        // ---------------- 3b. loss and its gradient w.r.t. the logits, one row per lane of warp 0 ----------------
+        // ---------------- 3b. loss and its gradient w.r.t. the logits ----------------
+        // BEAR: the six lgamma / digamma differences of a row (five letters + the total) are independent, so six
+        // warps evaluate one term each for the tile's rows (lane = row) instead of one warp walking all six.
+        if (MODE == MODE_TRAIN_BEAR && warp < A1 + 1) {
+            const int r = lane < TB ? lane : TB - 1;
+            const int64_t i = row0 + r;
+            const bool in_range = lane < TB && i < n;
+            double a, c;
+            if (warp < A1) {
+                a = fma(fbuf[r * A1 + warp], hinv, BEAR_EPS);                                   // bear_net.py:43
+                c = in_range ? double(__ldg(col + warp * stride + i)) : 0.0;
+            } else {
+                a = 0.0;
+                c = 0.0;
+#pragma unroll
+                for (int b2 = 0; b2 < A1; ++b2) {
+                    a += fma(fbuf[r * A1 + b2], hinv, BEAR_EPS);
+                    c += in_range ? double(__ldg(col + b2 * stride + i)) : 0.0;
+                }
+            }
+            const LgDg t = lgdg_diff<true>(a, c);
+            if (lane < TB) {
+                tbuf[(warp * TB + r) * 2] = t.add + (t.mul == 1.0 ? 0.0 : log(t.mul));
+                tbuf[(warp * TB + r) * 2 + 1] = t.dg;
+            }
+        }
+        if (MODE == MODE_TRAIN_BEAR) __syncthreads();
         if (warp == 0) {
             const int r = lane < TB ? lane : TB - 1;
             const int64_t i = row0 + r;
@@ -345,36 +376,30 @@ cnn_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ col,
             if (MODE == MODE_BWD) {
 #pragma unroll
                 for (int b = 0; b < A1; ++b) df[b] = in_range ? __ldg(gf_in + i * A1 + b) : 0.0;
-            } else {
+            } else if (MODE == MODE_TRAIN_AR) {
                 const Counts cr = load_counts(col, stride, i, in_range);
-                const bool live = cr.cmax != 0;
-                const uint32_t steps = warp_steps(live, cr.cmax);
-                double add, prod, ll = 0.0;
-                if (MODE == MODE_TRAIN_AR) {
-                    double pr[A1];
+                double add, prod, pr[A1];
 #pragma unroll
-                    for (int b = 0; b < A1; ++b) pr[b] = f[b] + BEAR_EPS;                  // bear_net.py:68
-                    mn_term(pr, cr, add, prod);
+                for (int b = 0; b < A1; ++b) pr[b] = f[b] + BEAR_EPS;                      // bear_net.py:68
+                mn_term(pr, cr, add, prod);
 #pragma unroll
-                    for (int b = 0; b < A1; ++b) df[b] = cr.c[b] == 0 ? 0.0 : double(cr.c[b]) / pr[b];
-                } else {
-                    double conc[A1], w[A1], tadd, tprod, tdg;
+                for (int b = 0; b < A1; ++b) df[b] = cr.c[b] == 0 ? 0.0 : double(cr.c[b]) / pr[b];
+                const double ll = cr.cmax != 0 ? add + log(prod) : 0.0;
+                ll_sum += ll;
+                if (ll_out && in_range) ll_out[i] = ll;
+            } else {
+                // ll = sum_b [lgamma(conc_b + c_b) - lgamma(conc_b)] - [lgamma(S + N) - lgamma(S)]; zero-count rows
+                // give exact zeros in every term
+                const double on = lane < TB ? 1.0 : 0.0;      // 16-row tiles: the upper half-warp has no row
+                const double tdg = tbuf[(A1 * TB + r) * 2 + 1];
+                double ll = -tbuf[(A1 * TB + r) * 2];
 #pragma unroll
-                    for (int b = 0; b < A1; ++b) conc[b] = fma(f[b], hinv, BEAR_EPS);       // bear_net.py:43
-                    letters_term<true>(stir, conc, cr, steps, add, prod, w);
-                    const double s = ((conc[0] + conc[1]) + (conc[2] + conc[3])) + conc[4];
-                    total_term<true>(s, cr, tadd, tprod, tdg);
-                    add -= tadd;
-                    prod /= tprod;
-                    if (live) {
-#pragma unroll
-                        for (int b = 0; b < A1; ++b) {
-                            df[b] = (w[b] - tdg) * hinv;
-                            dh_sum -= f[b] * df[b];
-                        }
-                    }
+                for (int b = 0; b < A1; ++b) {
+                    ll += tbuf[(b * TB + r) * 2];
+                    df[b] = on * (tbuf[(b * TB + r) * 2 + 1] - tdg) * hinv;
+                    dh_sum -= f[b] * df[b];
                 }
-                if (live) ll = add + log(prod);
+                ll *= on;
                 ll_sum += ll;
                 if (ll_out && in_range) ll_out[i] = ll;
             }
@@ -448,8 +473,8 @@ cnn_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ col,
         {
             double aS0 = 0.0, aI0 = 0.0;
             int curp = -1;
-            for (int idx = pair0; idx < pair1; ++idx) {
-                const int p = idx / TB, r = idx % TB;
+            for (int idx = pair0; idx < pair1; idx += 2) {
+                const int p = idx / TB, r = idx % TB;            // rows r and r + 1 at position p
                 if (p != curp) {
                     if (curp >= 0 && lane < d.F) {
                         atomicAdd(dsc0 + curp * d.F + lane, aS0);
@@ -458,27 +483,39 @@ cnn_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ col,
                     curp = p;
                     aS0 = aI0 = 0.0;
                 }
-                const uint16_t* so = soff + r * d.lag;
+                const uint16_t* soA = soff + r * d.lag;
+                const uint16_t* soB = soA + d.lag;
                 const bool fok = lane < d.F;
-                const double2 st = stats[idx];
-                const double xhat = fok ? (conv_at(fil, so, p, lane, d) - st.x) * st.y : 0.0;
-                const double dx0 = fok ? E0[r * d.es + p * d.F + lane] : 0.0;
-                aS0 = fma(dx0, xhat, aS0);
-                aI0 += dx0;
-                const double dxh = fok ? dx0 * sc0[p * d.F + lane] : 0.0;
-                double m1 = dxh, m2 = dxh * xhat;
-                warp_sum2(m1, m2);
-                const double dconv = st.y * (dxh - m1 * invF - xhat * (m2 * invF));
+                const double2 stA = stats[idx], stB = stats[idx + 1];
+                const double sc = fok ? sc0[p * d.F + lane] : 0.0;
+                const double xhA = fok ? (conv_at(fil, soA, p, lane, d) - stA.x) * stA.y : 0.0;
+                const double xhB = fok ? (conv_at(fil, soB, p, lane, d) - stB.x) * stB.y : 0.0;
+                const double dxA = fok ? E0[r * d.es + p * d.F + lane] : 0.0;
+                const double dxB = fok ? E0[(r + 1) * d.es + p * d.F + lane] : 0.0;
+                aS0 = fma(dxA, xhA, fma(dxB, xhB, aS0));
+                aI0 += dxA + dxB;
+                const double dhA = dxA * sc, dhB = dxB * sc;
+                double m1A = dhA, m2A = dhA * xhA, m1B = dhB, m2B = dhB * xhB;
+                warp_sum2(m1A, m2A);
+                warp_sum2(m1B, m2B);
+                const double dcA = stA.y * (dhA - m1A * invF - xhA * (m2A * invF));
+                const double dcB = stB.y * (dhB - m1B * invF - xhB * (m2B * invF));
                 if (fok) {
                     double* g = mydfil + lane;
                     const int ws = A1 * d.F;
                     if (d.W == 3) {
-                        g[so[p]] += dconv;
-                        g[ws + so[p + 1]] += dconv;
-                        g[2 * ws + so[p + 2]] += dconv;
+                        g[soA[p]] += dcA;
+                        g[ws + soA[p + 1]] += dcA;
+                        g[2 * ws + soA[p + 2]] += dcA;
+                        g[soB[p]] += dcB;
+                        g[ws + soB[p + 1]] += dcB;
+                        g[2 * ws + soB[p + 2]] += dcB;
                     } else {
 #pragma unroll 1
-                        for (int w = 0; w < d.W; ++w) g[w * ws + so[p + w]] += dconv;
+                        for (int w = 0; w < d.W; ++w) {
+                            g[w * ws + soA[p + w]] += dcA;
+                            g[w * ws + soB[p + w]] += dcB;
+                        }
                     }
                 }
             }

@@ -53,21 +53,21 @@ static __constant__ double kStirling[(SMALLC + 1) * (SMALLC + 1)] = {
     0, 720, 1764, 1624, 735, 175, 21, 1, 0,
     0, 5040, 13068, 13132, 6769, 1960, 322, 28, 1};
 
-template <bool GRAD>
-__device__ __forceinline__ void rf_letters(const double* __restrict__ stir, const double (&a)[A1], const uint32_t (&c)[A1],
+template <bool GRAD, typename TS>
+__device__ __forceinline__ void rf_letters(const TS* __restrict__ stir, const double (&a)[A1], const uint32_t (&c)[A1],
                                            uint32_t steps, double (&P)[A1], double (&D)[A1]) {
-    const double* row[A1];
+    const TS* row[A1];     // TS = float (exact: coefficients <= 13132) halves the shared-memory traffic, double saves the conversion
 #pragma unroll
     for (int b = 0; b < A1; ++b) {
         row[b] = stir + (c[b] <= SMALLC ? c[b] : 0u) * (SMALLC + 1);
-        P[b] = row[b][steps];
+        P[b] = double(row[b][steps]);
         D[b] = 0.0;
     }
     for (int k = int(steps) - 1; k >= 0; --k) {
 #pragma unroll
         for (int b = 0; b < A1; ++b) {
             if (GRAD) D[b] = fma(D[b], a[b], P[b]);
-            P[b] = fma(P[b], a[b], row[b][k]);
+            P[b] = fma(P[b], a[b], double(row[b][k]));
         }
     }
 }
@@ -102,11 +102,11 @@ __device__ __forceinline__ double inv5(const double (&d)[A1], double (&r)[A1]) {
 // sum_b [lgamma(conc_b + c_b) - lgamma(conc_b)] = add + log(prod) and, with GRAD, w_b = the digamma
 // differences.  Small counts: predicated rising factorials and one shared division; a lane with a
 // count above SMALLC redoes its row with the general routine (divergent, rare in sparse tables).
-template <bool GRAD>
-__device__ __forceinline__ void letters_term(const double* __restrict__ stir, const double (&conc)[A1], const Counts& r,
+template <bool GRAD, typename TS>
+__device__ __forceinline__ void letters_term(const TS* __restrict__ stir, const double (&conc)[A1], const Counts& r,
                                              uint32_t steps, double& add, double& prod, double (&w)[A1]) {
     double P[A1], D[A1];
-    rf_letters<GRAD>(stir, conc, r.c, steps, P, D);
+    rf_letters<GRAD, TS>(stir, conc, r.c, steps, P, D);
     add = 0.0;
     if (GRAD) {
         double ri[A1];

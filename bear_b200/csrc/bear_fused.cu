@@ -343,7 +343,7 @@ linear_train2_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restr
     uint16_t* symtab = reinterpret_cast<uint16_t*>(smem_raw + L.symtab);
     double* tab_lg = reinterpret_cast<double*>(smem_raw + L.tab_lg);
     double* tab_dg = reinterpret_cast<double*>(smem_raw + L.tab_dg);
-    double* stir = reinterpret_cast<double*>(smem_raw + L.stir);
+    float* stir = reinterpret_cast<float*>(smem_raw + L.stir);
     double* red = reinterpret_cast<double*>(smem_raw + L.red);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -352,7 +352,7 @@ linear_train2_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restr
 
     // ---------------- tables ----------------
     for (int i = threadIdx.x; i < nch * ENT * 4; i += blockDim.x) G[i] = 0.0;
-    for (int i = threadIdx.x; i < STIR_N; i += blockDim.x) stir[i] = kStirling[i];
+    for (int i = threadIdx.x; i < STIR_N; i += blockDim.x) stir[i] = float(kStirling[i]);
     for (int i = threadIdx.x; i < 2 * tiles; i += blockDim.x) stage_m[i] = 0u;
     if (!TRAIN_AR && threadIdx.x < TABN) {
         // the concentrations of a row sum to 1/h + 5 eps whatever its k-mer (softmax sums to 1)
