@@ -96,6 +96,17 @@ __device__ __noinline__ LgDg lgdg_diff(double a, double c) {
     return r;
 }
 
+// lgamma(a + c) - lgamma(a) for a ROW-INDEPENDENT a (a BMM prior, the concentration sum 1/h + 5 eps) and a large
+// count: x = a + c >= 64, so three terms of the Stirling series are exact to 1e-16, and lgamma(a) enters as the
+// precomputed constant K = ln(2 pi)/2 - lgamma(a).  Only for a < 64 (then lgamma(a) is small next to the result and
+// nothing cancels); larger a go through lgdg_diff.
+#define BEAR_LARGE_C 64.0
+__device__ __forceinline__ double lg_shift_large(double a, double c, double K) {
+    const double x = a + c, rx = 1.0 / x, r2 = rx * rx;
+    return fma(x - 0.5, log(x), K - x) + rx * fma(r2, fma(r2, 1.0 / 1260.0, -1.0 / 360.0), 1.0 / 12.0);
+}
+__device__ __forceinline__ double lg_shift_const(double a) { return 0.91893853320467274178 - lgamma(a); }
+
 // Accumulates sum_i (add_i + log mul_i) with as few log() calls as possible.
 struct LogProd {
     double add = 0.0, mul = 1.0;

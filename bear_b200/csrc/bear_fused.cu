@@ -665,6 +665,31 @@ explicit_train_kernel(const uint32_t* __restrict__ col, int64_t stride, int64_t 
 }
 
 // ------------------------------------------------------------------------------------------------
+// dense counts against row-independent concentrations (BMM priors)
+// ------------------------------------------------------------------------------------------------
+template <int NA1>
+struct CountVec {
+    uint32_t c[NA1];
+};
+
+// lgamma(a + c) - lgamma(a) summed over the letters of one row (minus `total` handled by the caller) for a
+// row-independent a: small counts from the count table, large ones by the constant-a Stirling form
+template <int NA1>
+__device__ __forceinline__ double dense_letters(const CountVec<NA1>& cv, double a, const double* __restrict__ tab_k, double Ka) {
+    double s = 0.0;
+#pragma unroll
+    for (int b = 0; b < NA1; ++b)
+        s += cv.c[b] < uint32_t(TABN) ? tab_k[cv.c[b]] : lg_shift_large(a, double(cv.c[b]), Ka);
+    return s;
+}
+
+// the vanilla-BMM term of one evaluation row without a conditioning column (prior vk = van_k + eps)
+__device__ __noinline__ double van_dense_row(CountVec<A1> cv, double rn, double vk, const double* __restrict__ tv,
+                                             double Kv, double Kvt) {
+    return dense_letters<A1>(cv, vk, tv, Kv) - lg_shift_large(double(A1) * vk, rn, Kvt);
+}
+
+// ------------------------------------------------------------------------------------------------
 // evaluation
 // ------------------------------------------------------------------------------------------------
 // NH / NV bound the number of h values (H) and of BMM priors (V) of one launch.
@@ -687,7 +712,8 @@ eval_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ tes
     double* tab_ear = red + 32;                    // [NM][TABN]  lgamma(S0_k + N) - lgamma(S0_k)
     double* tab_van = tab_ear + NM * TABN;         // [NM][TABN]  lgamma(van_k + eps + c) - lgamma(van_k + eps)
     double* tab_vtot = tab_van + NM * TABN;        // [NM][TABN]  lgamma(5 (van_k + eps) + N) - lgamma(5 (van_k + eps))
-    double* stir = tab_vtot + NM * TABN;           // Stirling triangle
+    double* kconst = tab_vtot + NM * TABN;         // [3][NM] ln(2 pi)/2 - lgamma(a) of the three table families
+    double* stir = kconst + 3 * NM;                // Stirling triangle
     for (int i = threadIdx.x; i < STIR_N; i += blockDim.x) stir[i] = kStirling[i];
     if (LIN) build_ext_tables(head, R, symtab, lag, ck);
     double hinv[NH], van[NV];
@@ -695,6 +721,19 @@ eval_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ tes
     for (int k = 0; k < NH; ++k) hinv[k] = k < H ? 1.0 / d_h[k] : 1.0;
 #pragma unroll
     for (int k = 0; k < NV; ++k) van[k] = k < V ? d_van[k] : 1.0;
+    // constants of the row-independent terms for counts past the tables (lg_shift_large); kept in shared memory
+    bool fast_van = true, fast_ear = true;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) fast_van = fast_van && double(A1) * (van[k] + BEAR_EPS) < BEAR_LARGE_C;
+#pragma unroll
+    for (int k = 0; k < NH; ++k) fast_ear = fast_ear && (HEAD == BEAR_HEAD_NONE ? 0.0 : hinv[k]) + A1 * BEAR_EPS < BEAR_LARGE_C;
+    if (!HAS_TRAIN && threadIdx.x < NM) {
+        const int k = threadIdx.x;
+        const double hk = k < H ? 1.0 / d_h[k] : 1.0, vk = (k < V ? d_van[k] : 1.0) + BEAR_EPS;
+        kconst[k] = lg_shift_const((HEAD == BEAR_HEAD_NONE ? 0.0 : hk) + A1 * BEAR_EPS);
+        kconst[NM + k] = lg_shift_const(vk);
+        kconst[2 * NM + k] = lg_shift_const(double(A1) * vk);
+    }
     if (!HAS_TRAIN) {
         for (int idx = threadIdx.x; idx < NM * TABN; idx += blockDim.x) {
             const int k = idx / TABN;
@@ -782,6 +821,8 @@ eval_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ tes
                 letters_term<false>(stir, conc, r, steps, add, prod, dummy);
                 if (TOT_TAB && use_tab) {
                     add -= tab_ear[k * TABN + int(r.n)];
+                } else if (TOT_TAB && fast_ear) {
+                    add -= lg_shift_large((HEAD == BEAR_HEAD_NONE ? 0.0 : hinv[k]) + A1 * BEAR_EPS, r.n, kconst[k]);
                 } else {
                     double tadd, tprod, tdg;
                     const double s = ((conc[0] + conc[1]) + (conc[2] + conc[3])) + conc[4];
@@ -820,6 +861,12 @@ eval_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ tes
                         const double* tv = tab_van + k * TABN;
                         van_add[k] += (((tv[r.c[0]] + tv[r.c[1]]) + (tv[r.c[2]] + tv[r.c[3]])) + tv[r.c[4]]) -
                                       tab_vtot[k * TABN + int(r.n)];
+                    } else if (fast_van) {
+                        CountVec<A1> cv;
+#pragma unroll
+                        for (int b = 0; b < A1; ++b) cv.c[b] = r.c[b];
+                        van_add[k] += van_dense_row(cv, r.n, van[k] + BEAR_EPS, tab_van + k * TABN, kconst[NM + k],
+                                                    kconst[2 * NM + k]);
                     } else {
                         LogProd num, den;
                         den.push(lgdg_diff<false>(((conc[0] + conc[1]) + (conc[2] + conc[3])) + conc[4], r.n));
@@ -894,11 +941,15 @@ bmm_kernel(const uint32_t* __restrict__ counts, int64_t stride, int64_t n, int G
     __shared__ double tab_tot[NV][TABN];  // lgamma(A1 a + N) - lgamma(A1 a)
     const int g = blockIdx.y;
     const uint32_t* col = counts + int64_t(g) * NA1 * stride;
-    double alpha[NV], acc[NV];
+    double alpha[NV], acc[NV], Ka[NV], Kt[NV];   // K = ln(2 pi)/2 - lgamma(a): constants of lg_shift_large
+    bool fast = true;               // every prior small enough for the constant-a Stirling form
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
         alpha[k] = k < V ? d_alpha[k] : 1.0;
         acc[k] = 0.0;
+        Ka[k] = lg_shift_const(alpha[k]);
+        Kt[k] = lg_shift_const(double(NA1) * alpha[k]);
+        fast = fast && double(NA1) * alpha[k] < BEAR_LARGE_C;
     }
     for (int idx = threadIdx.x; idx < NV * TABN; idx += blockDim.x) {
         const int k = idx / TABN;
@@ -925,6 +976,21 @@ bmm_kernel(const uint32_t* __restrict__ counts, int64_t stride, int64_t n, int G
 #pragma unroll
                     for (int b = 0; b < NA1; ++b) s += tab[k][c[b]];
                     acc[k] += s - tab_tot[k][toti];
+                }
+            }
+        } else if (fast) {
+            // dense counts: small letters from the table, large ones (and the total) by the constant-a Stirling form
+            double tot = 0.0;
+#pragma unroll
+            for (int b = 0; b < NA1; ++b) tot += double(c[b]);
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+                if (k < V) {
+                    double s = -lg_shift_large(double(NA1) * alpha[k], tot, Kt[k]);
+#pragma unroll
+                    for (int b = 0; b < NA1; ++b)
+                        s += c[b] < uint32_t(TABN) ? tab[k][c[b]] : lg_shift_large(alpha[k], double(c[b]), Ka[k]);
+                    acc[k] += s;
                 }
             }
         } else {
@@ -989,7 +1055,7 @@ int grid_for(int64_t n, int cap = MAX_GRID) {
 
 
 size_t eval_smem_bytes(int head, int lag, int nm) {
-    size_t d = 32 + size_t(3) * nm * TABN + STIR_N;
+    size_t d = 32 + size_t(3) * nm * TABN + 3 * nm + STIR_N;
     if (head == BEAR_HEAD_LINEAR) d += size_t(num_chunks(lag)) * ENT * 4 + (2 * ENT * 2) / 8;
     return sizeof(double) * d;
 }
