@@ -61,9 +61,9 @@ __device__ __forceinline__ int symbol_at(uint64_t v, int j, int lag, int nstart)
     return j < nstart ? 4 : int((v >> (2 * (lag - 1 - j))) & 3u);
 }
 
-__device__ __forceinline__ double pick5(const uint32_t (&c)[A1], int idx) {
-    const uint32_t v = idx == 0 ? c[0] : idx == 1 ? c[1] : idx == 2 ? c[2] : idx == 3 ? c[3] : c[4];
-    return double(v);
+// count of letter idx; the evaluation sums these as integers (exact, and no int -> double conversion per row)
+__device__ __forceinline__ uint32_t pick5(const uint32_t (&c)[A1], int idx) {
+    return idx == 0 ? c[0] : idx == 1 ? c[1] : idx == 2 ? c[2] : idx == 3 ? c[3] : c[4];
 }
 
 // argmax of v + sigma * N(0,1) (core.py:69-71,134-136).  Candidates are the entries within 16 sigma of
@@ -417,11 +417,8 @@ linear_train2_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restr
                             c0 += rr;
                             // rank of this row among the tile's rows with the same key: consumers apply rank 0 rows,
                             // then rank 1 rows, ... so equal keys never meet in one read-modify-write round
+                            // (match.any is slow: the table gather below is issued before its result is used)
                             const unsigned grp = __match_any_sync(0xffffffffu, live ? q : 0x10000 + lane);
-                            const int rank = __popc(grp & ((1u << lane) - 1u));
-                            const int maxr = __reduce_max_sync(0xffffffffu, live ? rank : 0);
-                            sq[ch * 32] = uint16_t(q | (rank << 10));
-                            if (lane == 0) stage_r[(buf * tiles + slot) * nch + ch] = uint8_t(maxr);
                             const int sw = half_swizzle(q);
                             const double2 a = *reinterpret_cast<const double2*>(R + (ch * ENT + q) * 4 + sw);
                             const double2 b = *reinterpret_cast<const double2*>(R + (ch * ENT + q) * 4 + (sw ^ 2));
@@ -429,6 +426,10 @@ linear_train2_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restr
                             p1 *= a.y;
                             p2 *= b.x;
                             p3 *= b.y;
+                            const int rank = __popc(grp & ((1u << lane) - 1u));
+                            const int maxr = __reduce_max_sync(0xffffffffu, live ? rank : 0);
+                            sq[ch * 32] = uint16_t(q | (rank << 10));
+                            if (lane == 0) stage_r[(buf * tiles + slot) * nch + ch] = uint8_t(maxr);
                         }
                         const double z = 1.0 + ((p0 + p1) + (p2 + p3));
                         if (z < 1e300 && z > 1e-300) {
@@ -750,13 +751,20 @@ eval_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ tes
     }
     __syncthreads();
 
-    double ear_add[NH], cor_ear[NH], van_add[NV], cor_van[NV];
+    double ear_add[NH], van_add[NV];
+    unsigned long long cor_ear[NH], cor_van[NV], cor_arm = 0ull;      // test counts at the predicted letters
     LogProdLong ear_prod[NH];
 #pragma unroll
-    for (int k = 0; k < NH; ++k) ear_add[k] = cor_ear[k] = 0.0;
+    for (int k = 0; k < NH; ++k) {
+        ear_add[k] = 0.0;
+        cor_ear[k] = 0ull;
+    }
 #pragma unroll
-    for (int k = 0; k < NV; ++k) van_add[k] = cor_van[k] = 0.0;
-    double arm_add = 0.0, cor_arm = 0.0, total = 0.0;
+    for (int k = 0; k < NV; ++k) {
+        van_add[k] = 0.0;
+        cor_van[k] = 0ull;
+    }
+    double arm_add = 0.0, total = 0.0;
     LogProdLong arm_prod;
 
     // the k-mer and test counts of the next row are fetched while the current row is evaluated
@@ -921,11 +929,11 @@ eval_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ tes
         if (k < V) { const double s = block_sum(van_add[k], red); if (threadIdx.x == 0) out[o] = s; ++o; }
 #pragma unroll
     for (int k = 0; k < NH; ++k)
-        if (k < H) { const double s = block_sum(cor_ear[k], red); if (threadIdx.x == 0) out[o] = s; ++o; }
-    { const double s = block_sum(cor_arm, red); if (threadIdx.x == 0) out[o] = s; ++o; }
+        if (k < H) { const double s = block_sum(double(cor_ear[k]), red); if (threadIdx.x == 0) out[o] = s; ++o; }
+    { const double s = block_sum(double(cor_arm), red); if (threadIdx.x == 0) out[o] = s; ++o; }
 #pragma unroll
     for (int k = 0; k < NV; ++k)
-        if (k < V) { const double s = block_sum(cor_van[k], red); if (threadIdx.x == 0) out[o] = s; ++o; }
+        if (k < V) { const double s = block_sum(double(cor_van[k]), red); if (threadIdx.x == 0) out[o] = s; ++o; }
     { const double s = block_sum(total, red); if (threadIdx.x == 0) out[o] = s; }
 }
 

@@ -96,6 +96,31 @@ def test_bmm_likelihood_known_answer(cuda):
     assert np.allclose(got2, want, rtol=1e-11, atol=0)
 
 
+def test_bmm_and_evaluation_count_regimes(cuda):
+    """Counts on both sides of the per-CTA tables (64), rows mixing table letters with large letters, priors below
+    and above the range of the constant-a Stirling form (5 alpha < 64), and huge counts: BMM table and the
+    no-conditioning evaluation against the oracle."""
+    from bear_b200 import bear_net, dataloader as dl
+    O = _oracle()
+    rng = np.random.default_rng(21)
+    K, lag = 4096, 6
+    codes, _ = synth_table(K, lag, 1, seed=4)
+    counts = np.zeros((K, 2, 5), dtype=np.int64)
+    counts[:, 0] = rng.integers(0, 3, size=(K, 5)) * rng.choice([1, 31, 32, 63, 64, 65, 1000, 250000, 4000000000 // 3], size=(K, 5))
+    counts[:, 1] = rng.poisson(1.0, size=(K, 5)) * rng.choice([1, 70], size=(K, 5))
+    counts[::7] = 0
+    data = make_dataset(codes, counts, lag, 1000)
+    alpha = np.array([0.05, 1.0, 12.0, 13.5, 300.0])
+    got = dl.bmm_likelihood(data, alpha).numpy()
+    want = O.bmm_likelihood(counts.astype(np.float64), alpha).numpy()
+    assert rel_err(got, want) <= LL_RTOL
+    for van in ([0.5, 2.0, 12.7], [40.0]):
+        for h in (0.05, 1.0, 100.0):
+            out = bear_net.evaluation(data, -1, 0, 'dna', h, None, van, seed=-1)
+            ref = _oracle_eval(codes, counts, lag, 0, -1, [h], van, None)
+            assert rel_err(out[0].numpy(), ref[0].numpy()) <= LL_RTOL and rel_err(out[2].numpy(), ref[2].numpy()) <= LL_RTOL
+
+
 def test_core_distributions(cuda):
     """reference tests/test_core.py:7-26,42-60 (broadcast conc [5, A+1] against counts [3, 5, A+1])"""
     from scipy.special import loggamma
