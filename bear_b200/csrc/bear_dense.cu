@@ -287,6 +287,50 @@ __global__ void synth_table_kernel(uint64_t* __restrict__ kmers, uint32_t* __res
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// compact transfer format -> packed table (include/bear_b200.h).  Four rows per thread: one 32-bit load per byte
+// plane, 128-bit stores of the count planes.
+// ---------------------------------------------------------------------------------------------
+__global__ void expand_table_kernel(const uint8_t* __restrict__ comp, int64_t pitch, int64_t n, int kb, int kbits_dna_lag,
+                                    int nplanes, uint64_t* __restrict__ kmers, uint32_t* __restrict__ counts,
+                                    int64_t stride, bool vec) {
+    const int64_t q = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;       // rows 4q .. 4q+3
+    const int64_t i0 = q * 4;
+    if (i0 >= n) return;
+    uint64_t v[4] = {0, 0, 0, 0};
+    for (int b = 0; b < kb; ++b) {
+        const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(comp + int64_t(b) * pitch) + q);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] |= uint64_t((w >> (8 * j)) & 0xffu) << (8 * b);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (kbits_dna_lag > 0) {        // DNA / RNA: n_start sits above the 2*lag payload bits
+            const uint64_t pay = v[j] & ((uint64_t(1) << (2 * kbits_dna_lag)) - 1);
+            v[j] = pay | ((v[j] >> (2 * kbits_dna_lag)) << 58);
+        }
+        if (i0 + j < n) kmers[i0 + j] = v[j];
+    }
+    for (int pl = 0; pl < nplanes; ++pl) {
+        const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(comp + (int64_t(kb) + pl) * pitch) + q);
+        uint32_t* dst = counts + int64_t(pl) * stride + i0;
+        if (vec && i0 + 3 < n) {
+            *reinterpret_cast<uint4*>(dst) = make_uint4(w & 0xffu, (w >> 8) & 0xffu, (w >> 16) & 0xffu, w >> 24);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (i0 + j < n) dst[j] = (w >> (8 * j)) & 0xffu;
+        }
+    }
+}
+
+__global__ void expand_escapes_kernel(const uint32_t* __restrict__ esc, int64_t n_esc, uint32_t* __restrict__ counts,
+                                      int64_t stride) {
+    const int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= n_esc) return;
+    counts[int64_t(esc[3 * e]) * stride + esc[3 * e + 1]] = esc[3 * e + 2];
+}
+
 }  // namespace
 
 #define ST(stream) static_cast<cudaStream_t>(stream)
@@ -403,5 +447,30 @@ extern "C" int bear_synth_table(uint64_t* d_kmers, uint32_t* d_counts, int64_t s
     synth_table_kernel<<<blocks_for(n), THREADS, 0, ST(stream)>>>(d_kmers, d_counts, stride, row_begin, n, lag, G, seed,
                                                                   regime, start_permille);
     BEAR_LAUNCH_CHECK("synth_table_kernel");
+    return BEAR_OK;
+}
+
+extern "C" int bear_expand_table(const uint8_t* d_compact, const uint32_t* d_esc, int64_t n_esc, int64_t n, int lag,
+                                 int alphabet, int G, uint64_t* d_kmers, uint32_t* d_counts, int64_t stride,
+                                 int64_t dst_row0, void* stream) {
+    const char* fn = "bear_expand_table";
+    const int a = bear_alphabet_size(alphabet);
+    BEAR_REQUIRE(a > 0 && lag >= 1 && lag <= bear_max_lag(alphabet) && G >= 1, fn);
+    BEAR_REQUIRE(n >= 0 && n_esc >= 0 && dst_row0 >= 0 && stride >= dst_row0 + n, fn);
+    if (n == 0) return BEAR_OK;
+    BEAR_REQUIRE(d_compact && d_kmers && d_counts && (d_esc || n_esc == 0), fn);
+    const bool dna = alphabet != BEAR_ALPHABET_PROT;
+    const int kb = ((dna ? 2 * lag + 6 : 5 * lag) + 7) / 8;
+    const int64_t pitch = (n + 15) / 16 * 16;
+    const int64_t quads = (n + 3) / 4;
+    const bool vec = (dst_row0 & 3) == 0 && (stride & 3) == 0 && (reinterpret_cast<uintptr_t>(d_counts) & 15) == 0;
+    expand_table_kernel<<<unsigned((quads + THREADS - 1) / THREADS), THREADS, 0, ST(stream)>>>(
+        d_compact, pitch, n, kb, dna ? lag : 0, G * (a + 1), d_kmers + dst_row0, d_counts + dst_row0, stride, vec);
+    BEAR_LAUNCH_CHECK("expand_table_kernel");
+    if (n_esc > 0) {
+        expand_escapes_kernel<<<unsigned((n_esc + THREADS - 1) / THREADS), THREADS, 0, ST(stream)>>>(d_esc, n_esc,
+                                                                                                  d_counts + dst_row0, stride);
+        BEAR_LAUNCH_CHECK("expand_escapes_kernel");
+    }
     return BEAR_OK;
 }

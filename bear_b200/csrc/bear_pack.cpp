@@ -447,3 +447,92 @@ extern "C" int bear_pack_sparse(const char* path, int header, int alphabet, int 
     return pack_file("bear_pack_sparse", path, header, alphabet, num_ds, first_row, max_rows, h_kmers, h_counts, stride,
                      rows_out, lag_out, true);
 }
+
+// ------------------------------------------------------------------------------------------------
+// compact transfer format (see include/bear_b200.h)
+// ------------------------------------------------------------------------------------------------
+static inline int compact_kbits(int lag, int alphabet) { return alphabet == BEAR_ALPHABET_PROT ? 5 * lag : 2 * lag + 6; }
+static inline int64_t compact_pitch(int64_t n) { return (n + 15) / 16 * 16; }
+
+extern "C" int64_t bear_compact_bytes(int64_t n, int lag, int alphabet, int G) {
+    const int a = bear_alphabet_size(alphabet);
+    if (a <= 0 || n < 0 || lag < 1 || lag > bear_max_lag(alphabet) || G < 1) return -1;
+    const int kb = (compact_kbits(lag, alphabet) + 7) / 8;
+    return compact_pitch(n) * (kb + int64_t(G) * (a + 1));
+}
+
+extern "C" int bear_compact_table(const uint64_t* h_kmers, const uint32_t* h_counts, int64_t stride, int64_t row0,
+                                  int64_t n, int lag, int alphabet, int G, uint8_t* h_out, uint32_t* h_esc,
+                                  int64_t esc_cap, int64_t* n_esc_out) {
+    const char* fn = "bear_compact_table";
+    const int a = bear_alphabet_size(alphabet);
+    BEAR_REQUIRE(a > 0 && lag >= 1 && lag <= bear_max_lag(alphabet) && G >= 1, fn);
+    BEAR_REQUIRE(n >= 0 && row0 >= 0 && stride >= row0 + n && n < (int64_t(1) << 32) && esc_cap >= 0, fn);
+    BEAR_REQUIRE(n_esc_out != nullptr, fn);
+    *n_esc_out = 0;
+    if (n == 0) return BEAR_OK;
+    BEAR_REQUIRE(h_kmers && h_counts && h_out && (h_esc || esc_cap == 0), fn);
+    const int A1 = a + 1, kb = (compact_kbits(lag, alphabet) + 7) / 8;
+    const int64_t pitch = compact_pitch(n);
+    const bool dna = alphabet != BEAR_ALPHABET_PROT;
+    const int nplanes = G * A1;
+    int nthreads = int(std::thread::hardware_concurrency());
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 16) nthreads = 16;
+    if (const char* e = getenv("BEAR_PACK_THREADS")) nthreads = atoi(e) > 0 ? atoi(e) : nthreads;
+    if (n < 65536) nthreads = 1;
+    // k-mer planes: rows split over threads
+    {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nthreads; ++t) {
+            pool.emplace_back([&, t]() {
+                const int64_t lo = n * t / nthreads, hi = n * (t + 1) / nthreads;
+                for (int64_t i = lo; i < hi; ++i) {
+                    const uint64_t code = h_kmers[row0 + i];
+                    const uint64_t v = dna ? ((code & ((uint64_t(1) << 58) - 1)) | ((code >> 58) << (2 * lag))) : code;
+                    for (int b = 0; b < kb; ++b) h_out[int64_t(b) * pitch + i] = uint8_t(v >> (8 * b));
+                }
+                for (int b = 0; b < kb; ++b)
+                    if (t == nthreads - 1)
+                        for (int64_t i = n; i < pitch; ++i) h_out[int64_t(b) * pitch + i] = 0;
+            });
+        }
+        for (auto& th : pool) th.join();
+    }
+    // count planes: one plane at a time per thread (keeps the escapes ordered by plane, row)
+    std::vector<std::vector<uint32_t>> esc(nplanes);
+    {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nthreads; ++t) {
+            pool.emplace_back([&, t]() {
+                for (int pl = t; pl < nplanes; pl += nthreads) {
+                    const uint32_t* src = h_counts + int64_t(pl) * stride + row0;
+                    uint8_t* dst = h_out + (int64_t(kb) + pl) * pitch;
+                    for (int64_t i = 0; i < n; ++i) {
+                        const uint32_t c = src[i];
+                        if (c >= 255u) {
+                            dst[i] = 255;
+                            esc[pl].push_back(uint32_t(pl));
+                            esc[pl].push_back(uint32_t(i));
+                            esc[pl].push_back(c);
+                        } else {
+                            dst[i] = uint8_t(c);
+                        }
+                    }
+                    for (int64_t i = n; i < pitch; ++i) dst[i] = 0;
+                }
+            });
+        }
+        for (auto& th : pool) th.join();
+    }
+    int64_t total = 0;
+    for (int pl = 0; pl < nplanes; ++pl) total += int64_t(esc[pl].size() / 3);
+    *n_esc_out = total;
+    if (total > esc_cap) return BEAR_OK;              // caller re-calls with room for *n_esc_out entries
+    int64_t o = 0;
+    for (int pl = 0; pl < nplanes; ++pl) {
+        if (!esc[pl].empty()) memcpy(h_esc + o * 3, esc[pl].data(), esc[pl].size() * sizeof(uint32_t));
+        o += int64_t(esc[pl].size() / 3);
+    }
+    return BEAR_OK;
+}

@@ -185,7 +185,7 @@ def run_ours(args, rank, world_size, local_rank):
     flat_params = torch.zeros(1 + P, dtype=torch.float64, device=dev)
     flat_params[1:] = mat.reshape(-1).to(dev)
     grad = torch.zeros(2 + P, dtype=torch.float64, device=dev)
-    m, v = torch.zeros_like(flat_params), torch.zeros_like(flat_params)
+    m_adam, v = torch.zeros_like(flat_params), torch.zeros_like(flat_params)
     step_ctr = torch.zeros(1, dtype=torch.int64, device=dev)
     ws = torch.empty(lib.bear_workspace_doubles(n, LAG, P), dtype=torch.float64, device=dev)
     hvals = torch.ones(1, dtype=torch.float64, device=dev)
@@ -207,7 +207,7 @@ def run_ours(args, rank, world_size, local_rank):
             train_events.append((e0, e1))
         if world_size > 1:
             dist.all_reduce(grad)
-        check(lib.bear_adam_update(ptr(flat_params), ptr(grad[1:]), ptr(m), ptr(v), 1 + P, 0.01, 0.9, 0.999, 1e-7,
+        check(lib.bear_adam_update(ptr(flat_params), ptr(grad[1:]), ptr(m_adam), ptr(v), 1 + P, 0.01, 0.9, 0.999, 1e-7,
                                    ptr(step_ctr), _lib.stream()))
 
     def eval_pass(k_t, c_ptr, n_rows, pitch):
@@ -247,49 +247,81 @@ def run_ours(args, rank, world_size, local_rank):
     results = acc.cpu().tolist()
 
     # ---- e2e: the same step from HOST-resident (pinned) buffers, copies inside the timed region ----
+    # The host side holds the table in the library's compact transfer format (byte planes + escapes,
+    # include/bear_b200.h: 11 B per row here instead of 28 B); every step copies it H2D chunk by chunk on a copy
+    # stream, expands each chunk on the device (bear_expand_table) and trains on it while the next chunk is in flight.
+    import ctypes
     e_rows = min(args.e2e_rows, n)
     e_stride = (e_rows + 3) // 4 * 4
-    hk = torch.empty(e_stride, dtype=torch.int64).pin_memory()
-    hc = torch.empty((1, 5, e_stride), dtype=torch.int32).pin_memory()
-    hk.copy_(kmers[:e_stride])
-    hc.copy_(counts[:, :, :e_stride])
-    dk = torch.empty_like(hk, device=dev)
-    dc = torch.empty_like(hc, device=dev)
+    hk = np.ascontiguousarray(kmers[:e_stride].cpu().numpy())
+    hc = np.ascontiguousarray(counts[:, :, :e_stride].cpu().numpy())
+    dk = torch.zeros(e_stride, dtype=torch.int64, device=dev)
+    dc = torch.zeros((1, 5, e_stride), dtype=torch.int32, device=dev)
     out_host = torch.empty(2 + P + acc.numel(), dtype=torch.float64).pin_memory()
 
     copy_stream = torch.cuda.Stream(device=dev)
     n_chunks = 8
     bounds = [(e_rows * i // n_chunks) // 4 * 4 for i in range(n_chunks)] + [e_rows]
+    chunks = []                       # (lo, rows, pinned compact bytes, device buffers, pinned escapes, device escapes, n_esc)
+    for lo, hi in zip(bounds[:-1], bounds[1:]):
+        m = hi - lo
+        nb = lib.bear_compact_bytes(m, LAG, 0, 1)
+        hb = torch.empty(nb, dtype=torch.uint8).pin_memory()
+        cap = 1 << 16
+        while True:
+            esc = np.empty((cap, 3), dtype=np.uint32)
+            need = ctypes.c_int64(0)
+            check(lib.bear_compact_table(ptr(hk), ptr(hc), e_stride, lo, m, LAG, 0, 1, ctypes.c_void_p(hb.data_ptr()),
+                                         ptr(esc), cap, ctypes.byref(need)))
+            if need.value <= cap:
+                break
+            cap = int(need.value)
+        he = torch.from_numpy(esc[:need.value].view(np.int32).copy()).pin_memory() if need.value else None
+        dbs = [torch.empty_like(hb, device=dev) for _ in range(2)]            # double-buffered on the device
+        des = [torch.empty_like(he, device=dev) for _ in range(2)] if he is not None else [None, None]
+        chunks.append((lo, m, hb, dbs, he, des, int(need.value)))
+    del hk, hc
     col_d = ctypes_ptr(dc)
+    pending, state = {}, {'k': 0}
 
-    def e2e_step():
-        # H2D in chunks on a copy stream; the training kernel of chunk i overlaps the copy of chunk i+1
-        # (the kernels accumulate into the flat buffer, so a batch may arrive in pieces).
-        main = torch.cuda.current_stream()
-        copy_stream.wait_stream(main)
-        events = []
+    def issue_copies(slot):
+        """H2D of one step's input (all chunks) into device buffer set `slot`, on the copy stream."""
+        evs = []
         with torch.cuda.stream(copy_stream):
-            for lo, hi in zip(bounds[:-1], bounds[1:]):
-                top = e_stride if hi == e_rows else hi
-                dk[lo:top].copy_(hk[lo:top], non_blocking=True)
-                for b in range(5):           # contiguous 1-D pieces: plain cudaMemcpyAsync each
-                    dc[0, b, lo:top].copy_(hc[0, b, lo:top], non_blocking=True)
+            for lo, m, hb, dbs, he, des, ne in chunks:
+                dbs[slot].copy_(hb, non_blocking=True)
+                if he is not None:
+                    des[slot].copy_(he, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
-                events.append(ev)
+                evs.append(ev)
+        pending[slot] = evs
+
+    def e2e_step():
+        # every step copies its whole input H2D and reads its results back D2H; the copy of step s+1 is issued at the
+        # start of step s (the input does not depend on the results), so it overlaps the kernels of step s
+        main = torch.cuda.current_stream()
+        slot = state['k'] & 1
+        if slot not in pending:
+            issue_copies(slot)
+        events = pending.pop(slot)
+        issue_copies(slot ^ 1)
         grad.zero_()
-        for (lo, hi), ev in zip(zip(bounds[:-1], bounds[1:]), events):
+        for (lo, m, hb, dbs, he, des, ne), ev in zip(chunks, events):
             main.wait_event(ev)
-            check(lib.bear_linear_train_step(ptr(dk), col_d, e_stride, lo, hi - lo, LAG, ptr(flat_params[1:]),
+            check(lib.bear_expand_table(ptr(dbs[slot]), ptr(des[slot]), ne, m, LAG, 0, 1, ptr(dk), ptr(dc), e_stride, lo,
+                                        _lib.stream()))
+            check(lib.bear_linear_train_step(ptr(dk), col_d, e_stride, lo, m, LAG, ptr(flat_params[1:]),
                                              ptr(flat_params[:1]), scale, 0, ptr(grad), None, ptr(ws), _lib.stream()))
         if world_size > 1:
             dist.all_reduce(grad)
-        check(lib.bear_adam_update(ptr(flat_params), ptr(grad[1:]), ptr(m), ptr(v), 1 + P, 0.01, 0.9, 0.999, 1e-7,
+        check(lib.bear_adam_update(ptr(flat_params), ptr(grad[1:]), ptr(m_adam), ptr(v), 1 + P, 0.01, 0.9, 0.999, 1e-7,
                                    ptr(step_ctr), _lib.stream()))
         eval_pass(dk, col_d, e_rows, e_stride)
         out_host[:2 + P].copy_(grad, non_blocking=True)
         out_host[2 + P:].copy_(acc, non_blocking=True)
         main.synchronize()
+        state['k'] += 1
 
     for _ in range(2):
         e2e_step()
@@ -305,7 +337,7 @@ def run_ours(args, rank, world_size, local_rank):
     if world_size > 1:
         dist.all_reduce(e_dt, op=dist.ReduceOp.MAX)
     e2e_value = 2.0 * e_rows * world_size / float(e_dt)
-    h2d = hk.numel() * 8 + hc.numel() * 4
+    h2d = sum(c[2].numel() + (c[4].numel() * 4 if c[4] is not None else 0) for c in chunks)
     d2h = out_host.numel() * 8
 
     if rank != 0:
@@ -331,8 +363,9 @@ def run_ours(args, rank, world_size, local_rank):
                    'l2': 'inputs larger than L2 (%.1f GB per GPU per pass)' % (TRAIN_BYTES_PER_ROW * n / 1e9)},
         'clocks': clocks.summary(),
         'e2e': {'value': e2e_value, 'unit': 'k-mer transition rows/s', 'h2d_bytes_per_step': h2d,
-                'd2h_bytes_per_step': d2h, 'rows_per_gpu_per_step': e_rows},
-        'gpu_launches': args.steps * 6,
+                'd2h_bytes_per_step': d2h, 'rows_per_gpu_per_step': e_rows,
+                'host_format': 'compact transfer format (byte planes + escapes), %.1f B/row' % (h2d / e_rows)},
+        'gpu_launches': args.steps * 6,       # timed region: train + reduce, adam + bump, eval + reduce per step
         'roofline': {'bound': 'hbm', 'kernel': 'linear_train2_kernel<false>', 'achieved': achieved, 'peak': peak,
                      'unit': 'GB/s', 'frac': achieved / peak, 'traffic': TRAIN_DRAM_BYTES_PER_ROW_NCU * n,
                      'traffic_note': 'bytes per launch = ncu dram read+write per row (profiles/r1_train2_raw.csv) x rows',

@@ -90,6 +90,26 @@ int bear_encode_kmers(const char* h_text, int64_t n, int lag, int alphabet, uint
 int bear_decode_kmers(const uint64_t* h_kmers, int64_t n, int lag, int alphabet, char* h_text);
 
 /* ------------------------------------------------------------------------------------------
+ * Compact transfer format.  Host-to-device copies bound the end-to-end rate (28 B per row at PCIe speed), so a
+ * table can cross the bus as byte planes: ceil(kbits/8) planes for the k-mer (kbits = 2*lag + 6 for DNA/RNA --
+ * the 6 bits hold n_start --, 5*lag for protein) and one byte plane per count column and letter; a count
+ * >= 255 is stored as 255 plus an escape entry {plane, row, value}.  Lossless for any table.
+ * Plane pitch = n rounded up to 16 bytes; bear_compact_bytes() = the size of the byte planes of n rows.
+ * bear_compact_table (host, multi-threaded) writes rows [row0, row0+n) of a packed table into h_out and the
+ * escapes (sorted by plane, row) into h_esc[esc_cap][3]; *n_esc_out = entries needed (re-call with a larger
+ * capacity if it exceeds esc_cap).  bear_expand_table (device) restores rows [dst_row0, dst_row0+n) of the packed
+ * table d_kmers / d_counts (plane pitch `stride`) bit-exactly.  Replaces nothing in the reference (its loader
+ * re-parses text every epoch, dataloader.py:36-46); it is the wire format of dataloader.KmerTable uploads.
+ * ---------------------------------------------------------------------------------------- */
+int64_t bear_compact_bytes(int64_t n, int lag, int alphabet, int G);
+int bear_compact_table(const uint64_t* h_kmers, const uint32_t* h_counts, int64_t stride, int64_t row0, int64_t n,
+                       int lag, int alphabet, int G, uint8_t* h_out, uint32_t* h_esc, int64_t esc_cap,
+                       int64_t* n_esc_out);
+int bear_expand_table(const uint8_t* d_compact, const uint32_t* d_esc, int64_t n_esc, int64_t n, int lag,
+                      int alphabet, int G, uint64_t* d_kmers, uint32_t* d_counts, int64_t stride, int64_t dst_row0,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Device: unpacking to the reference's dense tensors (core.tf_one_hot core.py:156-174; the counts
  * tensor of dataloader.py:44-46).  Used by plugin AR heads and by API-compat iteration.
  * ---------------------------------------------------------------------------------------- */

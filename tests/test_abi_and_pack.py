@@ -212,3 +212,50 @@ def test_multithreaded_pack_equals_single_thread(tmp_path, monkeypatch):
     bad = _write(tmp_path, '\n'.join(lines) + '\n', 'bad.tsv')
     with pytest.raises(_lib.BearError, match='outside the alphabet'):
         dl.KmerTable.from_file(bad, 'dna', 2)
+
+
+def _decode_compact(buf, esc, n, lag, alphabet, G, A1):
+    """numpy reader of the compact transfer format (include/bear_b200.h)."""
+    kbits = 5 * lag if alphabet == 'prot' else 2 * lag + 6
+    kb, pitch = (kbits + 7) // 8, (n + 15) // 16 * 16
+    b = buf.numpy()
+    v = np.zeros(n, dtype=np.uint64)
+    for i in range(kb):
+        v |= b[i * pitch:i * pitch + n].astype(np.uint64) << np.uint64(8 * i)
+    if alphabet != 'prot':
+        pay = v & np.uint64((1 << (2 * lag)) - 1)
+        v = pay | ((v >> np.uint64(2 * lag)) << np.uint64(58))
+    counts = np.stack([b[(kb + pl) * pitch:(kb + pl) * pitch + n].astype(np.uint32) for pl in range(G * A1)])
+    for pl, row, val in esc.numpy().view(np.uint32).reshape(-1, 3):
+        assert counts[pl, row] == 255
+        counts[pl, row] = val
+    return v, counts.reshape(G, A1, n)
+
+
+@pytest.mark.parametrize('alphabet,lag,n', [('dna', 20, 1000), ('dna', 29, 77), ('dna', 1, 16), ('prot', 12, 333), ('rna', 5, 70000)])
+def test_compact_transfer_format_is_lossless(alphabet, lag, n, monkeypatch):
+    """Host side of the compact transfer format: byte planes + escapes decode back to the packed table bit for bit
+    (counts on both sides of 255, up to 2^32 - 1; start-padded k-mers; sub-ranges; threaded and single-threaded)."""
+    from bear_b200 import dataloader as dl
+    rng = np.random.default_rng(lag * 1000 + n)
+    A1 = (20 if alphabet == 'prot' else 4) + 1
+    G = 2
+    if alphabet == 'prot':
+        codes = rng.integers(0, 1 << (5 * lag), size=n, dtype=np.uint64)
+    else:
+        codes = rng.integers(0, 4 ** lag, size=n, dtype=np.uint64)
+        ns = np.where(rng.random(n) < 0.3, rng.integers(1, lag + 1, size=n), 0).astype(np.uint64)
+        for i in np.flatnonzero(ns):
+            codes[i] &= np.uint64((1 << (2 * (lag - int(ns[i])))) - 1)
+        codes |= ns << np.uint64(58)
+    counts = rng.integers(0, 4, size=(n, G, A1)) * rng.choice([1, 80, 85, 127, 128, 1000, 1431655765], size=(n, G, A1))
+    table = dl.KmerTable.from_arrays((codes, lag), counts, alphabet)
+    for threads in ('1', '4'):
+        monkeypatch.setenv('BEAR_PACK_THREADS', threads)
+        for r0, m in ((0, n), (3, n - 7), (n // 2, 1)):
+            buf, esc = table.compact_chunk(r0, m)
+            assert buf.numel() == table.compact_bytes(m)
+            k, c = _decode_compact(buf, esc, m, lag, alphabet, G, A1)
+            assert np.array_equal(k, table.kmers_host[r0:r0 + m])
+            assert np.array_equal(c, table.counts_host[:, :, r0:r0 + m])
+            assert esc.shape[0] == int((table.counts_host[:, :, r0:r0 + m] >= 255).sum())

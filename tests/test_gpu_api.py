@@ -293,3 +293,40 @@ def test_packed_shard_cache_trains_identically(cuda, tmp_path):
     ra = bear_net.train(a, 1365, 1, 0, 'dna', 5, ar_funcs.make_ar_func_linear, {}, 0.01, 'Adam', False, params_restart=p0)
     rb = bear_net.train(b, 1365, 1, 0, 'dna', 5, ar_funcs.make_ar_func_linear, {}, 0.01, 'Adam', False, params_restart=p0)
     assert torch.allclose(ra[0][1], rb[0][1], rtol=1e-12, atol=0) and float(ra[1]) == pytest.approx(float(rb[1]), rel=1e-12)
+
+
+@pytest.mark.parametrize('alphabet,lag,n', [('dna', 20, 100003), ('dna', 3, 5), ('prot', 7, 4097)])
+def test_upload_through_compact_format_is_bit_exact(cuda, alphabet, lag, n):
+    """KmerTable.device_tensors() crosses the bus as byte planes + escapes and is expanded on the device
+    (bear_expand_table): the resident table equals the host arrays bit for bit, padding rows are zero; a chunk can
+    also be expanded at an unaligned destination row."""
+    import numpy as np
+    import torch
+    from bear_b200 import _lib, dataloader as dl
+    from bear_b200._lib import lib, check, ptr
+    rng = np.random.default_rng(n)
+    A1 = (20 if alphabet == 'prot' else 4) + 1
+    if alphabet == 'prot':
+        codes = rng.integers(0, 1 << (5 * lag), size=n, dtype=np.uint64)
+    else:
+        codes = rng.integers(0, 4 ** lag, size=n, dtype=np.uint64)
+        ns = np.where(rng.random(n) < 0.2, rng.integers(1, lag + 1, size=n), 0).astype(np.uint64)
+        for i in np.flatnonzero(ns):
+            codes[i] &= np.uint64((1 << (2 * (lag - int(ns[i])))) - 1)
+        codes |= ns << np.uint64(58)
+    counts = rng.integers(0, 3, size=(n, 3, A1)) * rng.choice([1, 127, 255, 256, 4000000000 // 2], size=(n, 3, A1))
+    table = dl.KmerTable.from_arrays((codes, lag), counts, alphabet)
+    k, c = table.device_tensors()
+    assert np.array_equal(k.cpu().numpy().view(np.uint64), table.kmers_host)
+    assert np.array_equal(c.cpu().numpy().view(np.uint32), table.counts_host)
+    # expansion at an unaligned destination (scalar stores)
+    m = min(n, 1001)
+    buf, esc = table.compact_chunk(n - m, m)
+    k2 = torch.zeros(m + 8, dtype=torch.int64, device=cuda)
+    c2 = torch.zeros((3, A1, m + 8), dtype=torch.int32, device=cuda)
+    dbuf, desc = buf.to(cuda), (esc.to(cuda) if esc.numel() else None)
+    check(lib.bear_expand_table(ptr(dbuf), ptr(desc), esc.shape[0], m, lag, _lib.ALPHABET_IDS[alphabet], 3, ptr(k2), ptr(c2),
+                                m + 8, 3, _lib.stream()))
+    assert np.array_equal(k2[3:3 + m].cpu().numpy().view(np.uint64), table.kmers_host[n - m:n])
+    assert np.array_equal(c2[:, :, 3:3 + m].cpu().numpy().view(np.uint32), table.counts_host[:, :, n - m:n])
+    assert int(c2[:, :, :3].abs().sum()) == 0 and int(c2[:, :, 3 + m:].abs().sum()) == 0
