@@ -29,9 +29,8 @@ namespace {
 
 using namespace bear;
 
-constexpr int THREADS = 256;
-constexpr int NWARP = THREADS / 32;
-constexpr int MAX_TILES = 13;                    // 8x8 accumulator tiles of dW1 per warp
+// A CTA has NW = 16 warps when its tile fits shared memory (the kernel is latency-bound: more warps hide more), else 8.
+__host__ __device__ constexpr int max_tiles(int nw) { return nw == 16 ? 7 : 13; }   // 8x8 dW1 accumulator tiles per warp
 constexpr int MAX_SMEM = 227 * 1024;
 constexpr uint64_t PAYLOAD_MASK = (1ull << 58) - 1;
 
@@ -79,7 +78,7 @@ struct Layout {
 constexpr int SMALL_N = 16 + 16 + 8;             // int1[16], scale1[16], int2[8]
 constexpr int SMALLG_N = 16 * A1 + 8 + 16 + 16;  // dW2[16][5], dint2[8], dint1[16], dscale1[16]
 
-__host__ __device__ inline Layout make_layout(const CnnDims& d, int TB, bool train) {
+__host__ __device__ inline Layout make_layout(const CnnDims& d, int TB, bool train, int nw) {
     Layout L;
     int o = 0;
     L.e0 = o;    o += TB * d.es;
@@ -96,7 +95,7 @@ __host__ __device__ inline Layout make_layout(const CnnDims& d, int TB, bool tra
     L.soff = o;  o += even((TB * d.lag + 3) / 4);        // uint16 [TB][lag]: symbol * F
     L.fbuf = o;  o += train ? TB * A1 : 0;               // f, then d objective / d logits, of the tile's rows
     L.tbuf = o;  o += train ? (A1 + 1) * TB * 2 : 0;     // per row and term: lgamma difference, digamma difference
-    L.dfil = o;  o += train ? NWARP * even(d.nfil) : 0;
+    L.dfil = o;  o += train ? nw * even(d.nfil) : 0;
     L.dsc0 = o;  o += train ? even(d.PF) : 0;
     L.din0 = o;  o += train ? even(d.PF) : 0;
     L.smallg = o; o += train ? SMALLG_N : 0;
@@ -149,15 +148,16 @@ __device__ __forceinline__ void warp_sum2(double& a, double& b) {
 
 __device__ __forceinline__ double elu(double x) { return x > 0.0 ? x : exp(x) - 1.0; }   // tf.nn.elu: exp(x) - 1
 
-template <int MODE, int TB>
-__global__ void __launch_bounds__(THREADS, 1)
+template <int MODE, int TB, int NW>
+__global__ void __launch_bounds__(NW * 32, 1)
 cnn_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ col, int64_t stride, int64_t n,
            const CnnDims d, const double* __restrict__ params, const double* __restrict__ h_signed,
            const double* __restrict__ gf_in, double* __restrict__ f_out, double* __restrict__ ll_out,
            double* __restrict__ partials) {
     constexpr bool TRAIN = MODE != MODE_FWD;
+    constexpr int THREADS = NW * 32, NWARP = NW, MAX_TILES = max_tiles(NW);
     extern __shared__ __align__(16) double smem[];
-    const Layout L = make_layout(d, TB, TRAIN);
+    const Layout L = make_layout(d, TB, TRAIN, NW);
     double* E0 = smem + L.e0;
     double* W1s = smem + L.w1s;
     double* Y = smem + L.y;
@@ -224,7 +224,7 @@ cnn_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ col,
     double ll_sum = 0.0, dh_sum = 0.0;
 
     const int npairs = d.P * TB;
-    const int ppw = (npairs + NWARP - 1) / NWARP;
+    const int ppw = ((npairs + NWARP - 1) / NWARP + 1) & ~1;     // even: the conv stages take two pairs per trip
     const int pair0 = warp * ppw, pair1 = min(npairs, pair0 + ppw);
     const int nt_h = d.Hp >> 3;                       // 8-wide tiles across the H1 units
     const int nt_pf = d.PFp >> 3;                     // ... across the P*F conv features
@@ -300,11 +300,13 @@ cnn_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ col,
         __syncthreads();
 
         // ---------------- 3a. per row (half-warp, lane = H1 unit): LN, elu, dense 2, softmax ----------------
-        constexpr int NIT = TB / 16;
+        constexpr int RPW = TB / NW;                         // rows per warp in the per-row stages (1, 2 or 4)
+        constexpr int NIT = RPW >= 2 ? RPW / 2 : 1;
         double k_yhat[NIT], k_rstd[NIT], k_x1[NIT], k_e1[NIT];
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
-            const int r = warp * (TB / 8) + it * 2 + half;
+            const bool act = it * 2 + half < RPW;             // RPW = 1: the upper half-warp has no row
+            const int r = act ? warp * RPW + it * 2 + half : 0;
             const int64_t i = row0 + r;
             const double yv = hok ? Y[r * d.ws + hl] : 0.0;
             const double mean = half_sum(yv) * invH;
@@ -327,7 +329,7 @@ cnn_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ col,
                 z += f[b];
             }
             const double zi = 1.0 / z;
-            if (hl < A1) {
+            if (hl < A1 && act) {
                 const double v = (hl == 0 ? f[0] : hl == 1 ? f[1] : hl == 2 ? f[2] : hl == 3 ? f[3] : f[4]) * zi;
                 if (MODE == MODE_FWD) {
                     if (i < n) f_out[i * A1 + hl] = v;
@@ -416,12 +418,13 @@ cnn_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ col,
         // ---------------- 3c. dense 2 backward, elu', layer-norm backward -> dY over Y ----------------
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
-            const int r = warp * (TB / 8) + it * 2 + half;
+            const bool act = it * 2 + half < RPW;
+            const int r = act ? warp * RPW + it * 2 + half : 0;
             const double yhat = k_yhat[it], e1 = k_e1[it];
             double de1 = 0.0;
 #pragma unroll
             for (int b = 0; b < A1; ++b) {
-                const double g = fbuf[r * A1 + b];
+                const double g = act ? fbuf[r * A1 + b] : 0.0;
                 de1 = fma(w2[b], g, de1);
                 aW2[b] = fma(e1, g, aW2[b]);
                 aI2[b] += g;
@@ -432,7 +435,7 @@ cnn_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ col,
             const double dyh = dx1 * sc1_l;
             const double m1 = half_sum(dyh) * invH;
             const double m2 = half_sum(dyh * yhat) * invH;
-            if (hok) Y[r * d.ws + hl] = k_rstd[it] * (dyh - m1 - yhat * m2);
+            if (hok && act) Y[r * d.ws + hl] = k_rstd[it] * (dyh - m1 - yhat * m2);
         }
         __syncthreads();
 
@@ -589,46 +592,58 @@ __global__ void cnn_reduce_kernel(const double* __restrict__ partials, int nblk,
     out[p - p_begin] += mult * s;
 }
 
-// rows per tile for these dimensions: 32 if the shared-memory carve-up fits, else 16, else 0 (unsupported)
-int pick_tb(const CnnDims& d, bool train) {
-    if (d.W < 1 || d.P < 1 || d.F < 1 || d.F > 32 || d.H1 < 1 || d.H1 > 16 || d.lag > 29) return 0;
-    if (((d.PFp >> 3) * (d.Hp >> 3) + NWARP - 1) / NWARP > MAX_TILES) return 0;
-    if (size_t(make_layout(d, 32, train).total) * 8 <= size_t(MAX_SMEM)) return 32;
-    if (size_t(make_layout(d, 16, train).total) * 8 <= size_t(MAX_SMEM)) return 16;
-    return 0;
+// rows per tile and warps per CTA for these dimensions: the first of (32 rows, 16 warps), (32, 8), (16, 16), (16, 8)
+// whose shared-memory carve-up fits; {0, 0} = outside the fused kernel
+struct TileCfg {
+    int tb, nw;
+};
+TileCfg pick_cfg(const CnnDims& d, bool train) {
+    if (d.W < 1 || d.P < 1 || d.F < 1 || d.F > 32 || d.H1 < 1 || d.H1 > 16 || d.lag > 29) return {0, 0};
+    const int ntiles = (d.PFp >> 3) * (d.Hp >> 3);
+    for (int tb : {32, 16})
+        for (int nw : {16, 8}) {
+            if ((ntiles + nw - 1) / nw > max_tiles(nw)) continue;
+            if (size_t(make_layout(d, tb, train, nw).total) * 8 <= size_t(MAX_SMEM)) return {tb, nw};
+        }
+    return {0, 0};
 }
 
-template <int MODE, int TB>
+template <int MODE, int TB, int NW>
 int launch(cudaStream_t st, const uint64_t* kmers, const uint32_t* col, int64_t stride, int64_t n, const CnnDims& d,
            const double* params, const double* h_signed, const double* gf, double* f_out, double* ll_out,
            double* partials, int* grid_out) {
-    const size_t smem = size_t(make_layout(d, TB, MODE != MODE_FWD).total) * 8;
-    cudaError_t e = cudaFuncSetAttribute(cnn_kernel<MODE, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    const size_t smem = size_t(make_layout(d, TB, MODE != MODE_FWD, NW).total) * 8;
+    cudaError_t e = cudaFuncSetAttribute(cnn_kernel<MODE, TB, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) {
         bear_set_error("cudaFuncSetAttribute(cnn_kernel, %zu bytes) failed: %s", smem, cudaGetErrorString(e));
         return BEAR_ERR_CUDA;
     }
     const int64_t ntile = (n + TB - 1) / TB;
     const int grid = int(ntile < 148 ? ntile : 148);
-    cnn_kernel<MODE, TB><<<grid, THREADS, smem, st>>>(kmers, col, stride, n, d, params, h_signed, gf, f_out, ll_out, partials);
+    cnn_kernel<MODE, TB, NW><<<grid, NW * 32, smem, st>>>(kmers, col, stride, n, d, params, h_signed, gf, f_out, ll_out, partials);
     BEAR_LAUNCH_CHECK("cnn_kernel");
     *grid_out = grid;
     return BEAR_OK;
 }
 
 template <int MODE>
-int launch_tb(int tb, cudaStream_t st, const uint64_t* kmers, const uint32_t* col, int64_t stride, int64_t n,
-              const CnnDims& d, const double* params, const double* h_signed, const double* gf, double* f_out,
-              double* ll_out, double* partials, int* grid_out) {
-    return tb == 32 ? launch<MODE, 32>(st, kmers, col, stride, n, d, params, h_signed, gf, f_out, ll_out, partials, grid_out)
-                    : launch<MODE, 16>(st, kmers, col, stride, n, d, params, h_signed, gf, f_out, ll_out, partials, grid_out);
+int launch_cfg(TileCfg c, cudaStream_t st, const uint64_t* kmers, const uint32_t* col, int64_t stride, int64_t n,
+               const CnnDims& d, const double* params, const double* h_signed, const double* gf, double* f_out,
+               double* ll_out, double* partials, int* grid_out) {
+#define BEAR_CNN_GO(TB_, NW_) \
+    return launch<MODE, TB_, NW_>(st, kmers, col, stride, n, d, params, h_signed, gf, f_out, ll_out, partials, grid_out)
+    if (c.tb == 32 && c.nw == 16) BEAR_CNN_GO(32, 16);
+    if (c.tb == 32) BEAR_CNN_GO(32, 8);
+    if (c.nw == 16) BEAR_CNN_GO(16, 16);
+    BEAR_CNN_GO(16, 8);
+#undef BEAR_CNN_GO
 }
 
 }  // namespace
 
 extern "C" int bear_cnn_supported(int lag, int filter_width, int num_filters, int layer1_width) {
     if (lag < 1 || filter_width < 1 || filter_width > lag) return 0;
-    return pick_tb(make_dims(lag, filter_width, num_filters, layer1_width), true) != 0;
+    return pick_cfg(make_dims(lag, filter_width, num_filters, layer1_width), true).tb != 0;
 }
 
 extern "C" int64_t bear_cnn_num_params(int lag, int filter_width, int num_filters, int layer1_width) {
@@ -645,13 +660,13 @@ extern "C" int bear_cnn_head_forward(const uint64_t* d_kmers, int64_t row0, int6
     if (n == 0) return BEAR_OK;
     BEAR_REQUIRE(d_kmers && d_params && d_f, fn);
     const CnnDims d = make_dims(lag, filter_width, num_filters, layer1_width);
-    const int tb = pick_tb(d, false);
-    if (!tb) {
+    const TileCfg tb = pick_cfg(d, false);
+    if (!tb.tb) {
         bear_set_error("%s: dimensions outside the fused kernel (F <= 32, H1 <= 16, shared memory)", fn);
         return BEAR_ERR_RANGE;
     }
     int grid;
-    return launch_tb<MODE_FWD>(tb, static_cast<cudaStream_t>(stream), d_kmers + row0, nullptr, 0, n, d, d_params, nullptr,
+    return launch_cfg<MODE_FWD>(tb, static_cast<cudaStream_t>(stream), d_kmers + row0, nullptr, 0, n, d, d_params, nullptr,
                                nullptr, d_f, nullptr, nullptr, &grid);
 }
 
@@ -665,18 +680,18 @@ extern "C" int bear_cnn_train_step(const uint64_t* d_kmers, const uint32_t* d_co
     if (n == 0) return BEAR_OK;
     BEAR_REQUIRE(d_kmers && d_col && d_params && d_h_signed && d_flat && d_workspace, fn);
     const CnnDims d = make_dims(lag, filter_width, num_filters, layer1_width);
-    const int tb = pick_tb(d, true);
-    if (!tb) {
+    const TileCfg tb = pick_cfg(d, true);
+    if (!tb.tb) {
         bear_set_error("%s: dimensions outside the fused kernel (F <= 32, H1 <= 16, shared memory)", fn);
         return BEAR_ERR_RANGE;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int grid, rc;
     if (train_ar)
-        rc = launch_tb<MODE_TRAIN_AR>(tb, st, d_kmers + row0, d_col + row0, stride, n, d, d_params, d_h_signed, nullptr,
+        rc = launch_cfg<MODE_TRAIN_AR>(tb, st, d_kmers + row0, d_col + row0, stride, n, d, d_params, d_h_signed, nullptr,
                                       nullptr, d_ll_out, d_workspace, &grid);
     else
-        rc = launch_tb<MODE_TRAIN_BEAR>(tb, st, d_kmers + row0, d_col + row0, stride, n, d, d_params, d_h_signed, nullptr,
+        rc = launch_cfg<MODE_TRAIN_BEAR>(tb, st, d_kmers + row0, d_col + row0, stride, n, d, d_params, d_h_signed, nullptr,
                                         nullptr, d_ll_out, d_workspace, &grid);
     if (rc) return rc;
     const int P = 2 + d.nparams;
@@ -694,14 +709,14 @@ extern "C" int bear_cnn_head_backward(const uint64_t* d_kmers, int64_t row0, int
     if (n == 0) return BEAR_OK;
     BEAR_REQUIRE(d_kmers && d_params && d_gf && d_gparams && d_workspace, fn);
     const CnnDims d = make_dims(lag, filter_width, num_filters, layer1_width);
-    const int tb = pick_tb(d, true);
-    if (!tb) {
+    const TileCfg tb = pick_cfg(d, true);
+    if (!tb.tb) {
         bear_set_error("%s: dimensions outside the fused kernel (F <= 32, H1 <= 16, shared memory)", fn);
         return BEAR_ERR_RANGE;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int grid;
-    const int rc = launch_tb<MODE_BWD>(tb, st, d_kmers + row0, nullptr, 0, n, d, d_params, nullptr, d_gf, nullptr, nullptr,
+    const int rc = launch_cfg<MODE_BWD>(tb, st, d_kmers + row0, nullptr, 0, n, d, d_params, nullptr, d_gf, nullptr, nullptr,
                                        d_workspace, &grid);
     if (rc) return rc;
     const int P = 2 + d.nparams;

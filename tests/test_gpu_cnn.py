@@ -37,12 +37,14 @@ def split_block(flat, ps):
 
 
 DIMS = [            # lag, W, F, H1, rows
-    (13, 3, 30, 16, 6000),      # BASELINE C4 / config_files/bear_cnn_bear.cfg; > 148 tiles: several tiles per CTA
+    (13, 3, 30, 16, 6000),      # BASELINE C4 / config_files/bear_cnn_bear.cfg; 32-row tiles, 16 warps; > 148 tiles
     (13, 8, 30, 16, 700),       # the reference's default filter width (ar_funcs.py:50)
     (5, 3, 30, 16, 333),        # bundled example lag
     (9, 2, 7, 5, 1000),         # odd sizes: F and H1 not multiples of the tensor-core tile
-    (20, 8, 30, 16, 500),       # 16-row tiles (shared-memory bound)
+    (20, 8, 30, 16, 500),       # 16-row tiles, 8 warps (shared-memory bound)
     (6, 6, 32, 8, 200),         # a single conv position, all 32 lanes active
+    (16, 8, 30, 16, 400),       # 32-row tiles with 8 warps (the 16 warp-private filter-gradient tables do not fit)
+    (17, 3, 28, 16, 300),       # 16-row tiles with 16 warps (too many dW1 accumulator tiles for 8 warps)
 ]
 
 
