@@ -207,8 +207,8 @@ def train_loop(data, num_kmers, ds_loc, train_ar, acc_steps, fp, optimizer_name,
 
     Small tables make this loop launch-bound (the reference's tutorial: 10 000 steps over 1 365 rows), so when
     the step only launches libbear_b200 kernels (``graph_safe``) one epoch is captured in a CUDA graph
-    after an eager first epoch and replayed for the remaining ones (capture costs ~60 ms, so only runs of
-    >= 256 epochs use it)."""
+    after an eager first epoch and replayed for the remaining ones (capture costs ~0.2 s, so only runs of
+    >= BEAR_GRAPH_MIN_EPOCHS = 2048 epochs use it)."""
     opt = Optimizer(optimizer_name, learning_rate, fp.total, fp.flat.device)
     fp.grad.zero_()
     record = writer is not None or loss_save is not None
@@ -225,7 +225,8 @@ def train_loop(data, num_kmers, ds_loc, train_ar, acc_steps, fp, optimizer_name,
                 opt.apply(fp.flat, fp.grad[1:])
                 fp.grad.zero_()
 
-    use_graph = (graph_safe and fp.flat.is_cuda and world()[1] == 1 and reps >= 256 and 0 < nb <= 64
+    min_epochs = int(os.environ.get('BEAR_GRAPH_MIN_EPOCHS', 2048))       # capture costs ~0.2 s, replay saves ~80 us / epoch
+    use_graph = (graph_safe and fp.flat.is_cuda and world()[1] == 1 and reps >= min_epochs and 0 < nb <= 64
                  and nb % acc_steps == 0 and not os.environ.get('BEAR_NO_GRAPH'))
     if use_graph:
         upd = nb // acc_steps

@@ -487,6 +487,7 @@ def test_cuda_graph_replay_matches_eager_loop(cuda, monkeypatch):
     p0, _, _ = bear_net._create_params(5, 4, ar_funcs.make_ar_func_linear, {})
     p0 = [p.clone() for p in p0]
     runs = {}
+    monkeypatch.setenv('BEAR_GRAPH_MIN_EPOCHS', '256')
     for mode in ('graph', 'eager'):
         if mode == 'eager':
             monkeypatch.setenv('BEAR_NO_GRAPH', '1')

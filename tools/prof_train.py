@@ -32,3 +32,8 @@ for _ in range(2):
                              ptr(alpha), 3, 7, ptr(eacc), ptr(ws), _lib.stream()))
 torch.cuda.synchronize()
 print('ok', float(flat[0]))
+if os.environ.get('BMM'):
+    acc3 = torch.zeros(3, dtype=torch.float64, device=dev)
+    for _ in range(2):
+        check(lib.bear_bmm_likelihood(ptr(counts), stride, 0, n, 1, 5, ptr(alpha), 3, ptr(acc3), ptr(ws), _lib.stream()))
+    torch.cuda.synchronize()
