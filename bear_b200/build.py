@@ -29,6 +29,10 @@ NVCC_FLAGS = [
 ]
 
 
+# extra nvcc flags for kernel experiments, e.g. BEAR_NVCC_EXTRA=-DBEAR_TRAIN_EXPERIMENTS (part of the build digest)
+NVCC_FLAGS += os.environ.get('BEAR_NVCC_EXTRA', '').split()
+
+
 def _nvcc():
     for cand in (os.environ.get('NVCC'), shutil.which('nvcc'), '/usr/local/cuda/bin/nvcc'):
         if cand and os.path.exists(cand):

@@ -19,6 +19,7 @@
 // Reductions are two-stage and deterministic across CTAs: per-CTA partials in the caller's workspace,
 // then a fixed-order sum.
 #include <math.h>
+#include <stdlib.h>
 
 #include "bear_b200.h"
 #include "bear_common.cuh"
@@ -207,6 +208,16 @@ __device__ __forceinline__ void rmw_row(double* Gc, int q, double s0, double s1,
     *lo = a;
     *hi = b;
 }
+
+// Kernel experiments, compiled in with BEAR_NVCC_EXTRA=-DBEAR_TRAIN_EXPERIMENTS (bear_b200/build.py): with
+// BEAR_TRAIN_DEBUG=1 in the environment the consumers skip the scatter -- wrong results, timing of the producer side
+// only (tools/ab_train.py; profiles/README.md "Experiments")
+#ifdef BEAR_TRAIN_EXPERIMENTS
+__constant__ int g_train_debug = 0;
+#define BEAR_TRAIN_SKIP_SCATTER (g_train_debug != 0)
+#else
+#define BEAR_TRAIN_SKIP_SCATTER false
+#endif
 
 struct Train2Layout {                // offsets in bytes from the start of dynamic shared memory
     int R, G, stage_g, stage_q, stage_m, tags, symtab, tab_lg, tab_dg, stir, red, total;
@@ -535,7 +546,7 @@ linear_train2_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restr
                     n2 = sg[192 + lane];
                     n3 = sg[224 + lane];
                 }
-                if (m == 0u) continue;
+                if (m == 0u || BEAR_TRAIN_SKIP_SCATTER) continue;
                 bool todo = pend;
                 int plain = rounds;
                 if (rounds > 4) {
@@ -1132,6 +1143,10 @@ extern "C" int bear_linear_train_step(const uint64_t* d_kmers, const uint32_t* d
     const int64_t ntiles = (n + 31) / 32, per_cta = int64_t(T2_NW - nch) * tpw;
     const int64_t want = (ntiles + per_cta - 1) / per_cta;
     const int grid2 = int(want < 148 ? want : 148);
+#ifdef BEAR_TRAIN_EXPERIMENTS
+    static const int debug = getenv("BEAR_TRAIN_DEBUG") ? atoi(getenv("BEAR_TRAIN_DEBUG")) : 0;
+    if (debug) BEAR_CUDA_CHECK(cudaMemcpyToSymbolAsync(g_train_debug, &debug, sizeof(int), 0, cudaMemcpyHostToDevice, st));
+#endif
     if (train_ar) {
         if (set_smem(linear_train2_kernel<true>, smem2)) return BEAR_ERR_CUDA;
         linear_train2_kernel<true><<<grid2, T2_THREADS, smem2, st>>>(d_kmers + row0, d_col + row0, stride, n, lag, ck, tpw,

@@ -29,7 +29,7 @@ LAG = 20
 TRAIN_BYTES_PER_ROW = 28          # 8 B packed k-mer + 5 x 4 B counts (one column)  SURVEY.md 8(d)
 EVAL_BYTES_PER_ROW = 28           # ds_loc_train = -1: k-mer + the test column
 # dram__bytes_read.sum + dram__bytes_write.sum of linear_train2_kernel per row, from the ncu --set full capture
-# profiles/r1_train2_raw.csv (1.880 GB + 0.006 GB over 67 108 864 rows)
+# profiles/r1_fused_raw.csv (1.880 GB + 0.006 GB over 67 108 864 rows)
 TRAIN_DRAM_BYTES_PER_ROW_NCU = 28.10
 DEFAULT_ROWS = 1 << 31
 
@@ -141,7 +141,7 @@ def run_reference(args, rank):
     value = 2 * rows / dt
     cores = os.cpu_count() or 1
     sample = '%d synthetic lag-20 rows per step (train pass + eval pass), torch-CPU float64 oracle port' % rows
-    print(json.dumps({
+    print_result(json.dumps({
         'impl': 'reference', 'metric': 'kmer_transitions_per_s_train_plus_eval', 'value': value,
         'unit': 'k-mer transition rows/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
@@ -227,15 +227,28 @@ def run_ours(args, rank, world_size, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0.record()
     for _ in range(args.warmup):
         step()
+    w1.record()
     barrier()
+    # nvidia-smi answers in 0.1-0.3 s: when the K timed steps are shorter than ~1 s (small shards at N = 8) the same
+    # step keeps running AFTER the timed region has been closed (s1 recorded) so that the sampler sees the clocks
+    # under this load; the number of extra steps is the same on every rank (they contain the allreduce)
+    est = torch.tensor([w0.elapsed_time(w1) / max(args.warmup, 1)], dtype=torch.float64, device=dev)
+    if world_size > 1:
+        dist.all_reduce(est, op=dist.ReduceOp.MAX)
+    est_ms = max(float(est), 1e-3)
+    extra_steps = 0 if args.steps * est_ms >= 1000.0 else min(int((1000.0 - args.steps * est_ms) / est_ms) + 1, 400)
     with ClockSampler(local_rank) as clocks:
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record()
         for _ in range(args.steps):
             step(record=True)
         s1.record()
+        for _ in range(extra_steps):
+            step()
         barrier()
     ms = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
     if world_size > 1:
@@ -361,14 +374,15 @@ def run_ours(args, rank, world_size, local_rank):
                                'row-sharded over %d GPU(s); step = full-shard train pass + eval pass' % (rows_total, world_size),
                    'rows_total': rows_total, 'rows_per_gpu': n, 'lag': LAG, 'groups': 1,
                    'l2': 'inputs larger than L2 (%.1f GB per GPU per pass)' % (TRAIN_BYTES_PER_ROW * n / 1e9)},
-        'clocks': clocks.summary(),
+        'clocks': dict(clocks.summary(), sampled_over='the %d timed steps + %d identical untimed steps after them'
+                       % (args.steps, extra_steps)),
         'e2e': {'value': e2e_value, 'unit': 'k-mer transition rows/s', 'h2d_bytes_per_step': h2d,
                 'd2h_bytes_per_step': d2h, 'rows_per_gpu_per_step': e_rows,
                 'host_format': 'compact transfer format (byte planes + escapes), %.1f B/row' % (h2d / e_rows)},
         'gpu_launches': args.steps * 6,       # timed region: train + reduce, adam + bump, eval + reduce per step
         'roofline': {'bound': 'hbm', 'kernel': 'linear_train2_kernel<false>', 'achieved': achieved, 'peak': peak,
                      'unit': 'GB/s', 'frac': achieved / peak, 'traffic': TRAIN_DRAM_BYTES_PER_ROW_NCU * n,
-                     'traffic_note': 'bytes per launch = ncu dram read+write per row (profiles/r1_train2_raw.csv) x rows',
+                     'traffic_note': 'bytes per launch = ncu dram read+write per row (profiles/r1_fused_raw.csv) x rows',
                      'algorithmic_bytes': TRAIN_BYTES_PER_ROW * n,
                      'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s',
                      'kernel_ms': train_ms, 'bytes_per_row': TRAIN_BYTES_PER_ROW},
@@ -388,9 +402,13 @@ def run_ours(args, rank, world_size, local_rank):
                                 'cores': os.cpu_count() or 1, 'kind': 'port',
                                 'sample': '%d synthetic lag-20 rows x %d steps (train pass + eval pass), torch-CPU float64 '
                                           'oracle port of the reference TF graph' % (args.cpu_rows, reps)}
-    print(json.dumps(line))
+    print_result(json.dumps(line))
     if world_size > 1:
         dist.destroy_process_group()
+
+
+def print_result(line):          # replaced in main() by a writer on the saved stdout descriptor
+    print(line)
 
 
 def ctypes_ptr(t):
@@ -400,6 +418,17 @@ def ctypes_ptr(t):
 
 def main():
     args = parse()
+    # stdout carries exactly ONE line, the JSON result: libraries that print to file descriptor 1 (NCCL writes
+    # "NCCL version ..." there on communicator creation) are sent to stderr for the rest of the run
+    sys.stdout.flush()
+    result_fd = os.dup(1)
+    os.dup2(2, 1)
+    global print_result
+    result_out = os.fdopen(result_fd, 'w')
+
+    def print_result(line):
+        result_out.write(line + '\n')
+        result_out.flush()
     rank = int(os.environ.get('RANK', 0))
     world_size = int(os.environ.get('WORLD_SIZE', 1))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))

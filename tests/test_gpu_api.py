@@ -330,3 +330,35 @@ def test_upload_through_compact_format_is_bit_exact(cuda, alphabet, lag, n):
     assert np.array_equal(k2[3:3 + m].cpu().numpy().view(np.uint64), table.kmers_host[n - m:n])
     assert np.array_equal(c2[:, :, 3:3 + m].cpu().numpy().view(np.uint32), table.counts_host[:, :, n - m:n])
     assert int(c2[:, :, :3].abs().sum()) == 0 and int(c2[:, :, 3 + m:].abs().sum()) == 0
+
+
+def test_assemble_follows_the_counted_sequence(cuda, tmp_path):
+    """assemble_no_ends (reference assemble.py:21-184) with a BMM whose prior is tiny on a table counted from one
+    random sequence: every k-mer has a single successor, so generation from a seed reproduces the source sequence
+    forwards and -- on the reverse complement -- backwards, in MAP and in sampled mode; the reverse-strand counts
+    come either from the table (summarised with reverse=True) or from the counter's reverse-complement lookups."""
+    from bear_b200 import assemble, dataloader, summarize
+    rng = np.random.default_rng(3)
+    lag = 12
+    src = ''.join(rng.choice(list('ACGT'), size=600))
+    fa = tmp_path / 'seeds.fa'
+    fa.write_text('>seed0\n' + src[300:312] + '\n' + src[312:320] + '\n>seed1\n' + src[100:130] + '\n')
+    want = [src[270:360], src[90:135]]
+    both, _ = summarize.count_kmers([src], [0], lag, reverse=True)
+    fwd, _ = summarize.count_kmers([src], [0], lag, reverse=False)
+    for table, reverse, get_map in ((both, False, True), (both, False, False), (fwd, True, False)):
+        data = dataloader.KmerDataset(table, 1000)
+        out = tmp_path / ('out_%d_%d' % (reverse, get_map))
+        gen, ent = assemble.assemble_no_ends(str(fa), [[30, 40], [10, 5]], 3, None, van=1e-7, lag=lag, alphabet_name='dna',
+                                             data=data, reverse=reverse, get_map=get_map, seed=5, batch_size=4,
+                                             save_folder=str(out))
+        assert gen.shape == (2, 3)
+        for row, w in zip(gen, want):
+            assert all(s == w for s in row), (row, w)
+        assert all(np.allclose(e, 0.0) for e in ent) and len(ent[0]) == 90 and len(ent[1]) == 45
+        assert (out / 'seqs.fa').read_text().count('>') == 6
+    # a flat model (large prior, no counts to speak of) generates diverse sequences: per-site entropy near log 4
+    data = dataloader.KmerDataset(fwd, 1000)
+    gen, ent = assemble.assemble_no_ends([src[:lag]], [[0, 30]], 200, None, van=1e6, lag=lag, alphabet_name='dna',
+                                         data=data, reverse=True, seed=6)
+    assert len(set(gen[0])) > 150 and np.all(ent[0][lag:] > 1.2) and np.allclose(ent[0][:lag], 0.0)

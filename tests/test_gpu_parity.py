@@ -262,6 +262,30 @@ def test_linear_train_step_few_distinct_kmers(cuda):
     _check_train_step(cuda, codes, cnt, 9, 0, True, 0.1, seed=4)
 
 
+@pytest.mark.parametrize('lag', [13, 20])
+def test_linear_train_step_runs_of_equal_keys(cuda, lag):
+    """Rows in k-mer order share their leading chunk keys in runs: the consumer's segmented-scan path (one
+    read-modify-write per run).  Stray rows (out of order, start-padded) break the monotone order inside a tile, so
+    run ends with possibly equal keys take turns; zero-count rows sit inside runs; the trailing chunks have 32 keys
+    per tile and stay on the ranked path."""
+    rng = np.random.default_rng(40 + lag)
+    K = 5000
+    _, counts = synth_table(K, lag, 1, seed=lag)
+    prefix = np.uint64(int(rng.integers(0, 4 ** (lag - 11))) << 22)
+    codes = np.sort(rng.choice(1 << 22, size=K, replace=False)).astype(np.uint64) | prefix
+    stray = rng.choice(K, size=K // 40, replace=False)
+    codes[stray] = rng.integers(0, 4 ** lag, size=len(stray), dtype=np.uint64)
+    padded = rng.choice(K, size=K // 100, replace=False)
+    for i in padded:
+        ns = int(rng.integers(1, lag + 1))
+        codes[i] = (codes[i] & np.uint64((1 << (2 * (lag - ns))) - 1)) | (np.uint64(ns) << np.uint64(58))
+    for train_ar in (False, True):
+        _check_train_step(cuda, codes, counts, lag, 0, train_ar, 0.3, seed=lag)
+    # the same rows in sorted order without strays: monotone tiles only
+    plain = np.sort(rng.choice(1 << 22, size=K, replace=False)).astype(np.uint64) | prefix
+    _check_train_step(cuda, plain, counts, lag, 0, False, -0.4, seed=lag + 1)
+
+
 def test_linear_head_exact_fallback_on_extreme_logits(cuda):
     """Logit spreads of several hundred overflow the product of table ratios; the kernels then evaluate the
     max-subtracted softmax of that row directly.  Train step and evaluation stay finite and match the oracle."""
