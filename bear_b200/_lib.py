@@ -9,7 +9,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libbear_b200.so')
+# BEAR_B200_LIB: another build of the same library (kernel experiments, tools/experiments/build_exp.sh)
+LIB_PATH = os.environ.get('BEAR_B200_LIB') or os.path.join(_HERE, 'libbear_b200.so')
 
 MAX_MODELS = 8
 HEAD_NONE, HEAD_LINEAR, HEAD_EXPLICIT, HEAD_STOP = 0, 1, 2, 3

@@ -214,9 +214,15 @@ __device__ __forceinline__ void rmw_row(double* Gc, int q, double s0, double s1,
 // only (tools/ab_train.py; profiles/README.md "Experiments")
 #ifdef BEAR_TRAIN_EXPERIMENTS
 __constant__ int g_train_debug = 0;
+// [0] cycles the producer warps spent computing (summed over warps and CTAs), [1] the same for the consumer warps'
+// scatter, [2] cycles between the first and the last barrier summed over CTAs, [3] producer warps, [4] consumer warps:
+// busy fraction of a role = [0 or 1] / ([2] * warps of that role per CTA)
+__device__ unsigned long long g_train_cycles[5];
 #define BEAR_TRAIN_SKIP_SCATTER (g_train_debug != 0)
+#define BEAR_TRAIN_CLOCK() clock64()
 #else
 #define BEAR_TRAIN_SKIP_SCATTER false
+#define BEAR_TRAIN_CLOCK() 0ll
 #endif
 
 struct Train2Layout {                // offsets in bytes from the start of dynamic shared memory
@@ -388,8 +394,11 @@ linear_train2_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restr
     RowIn nxt;
     if (producer) nxt = load_row(kmers, col, stride, (tile_of(0, slot0) << 5) + lane, niter > 0 ? n : 0);
 
+    long long busy = 0;
+    const long long t_begin = BEAR_TRAIN_CLOCK();
     for (int64_t it = 0; it <= niter; ++it) {
         const int buf = int(it & 1);
+        const long long t_it = BEAR_TRAIN_CLOCK();
         if (producer) {
             if (it < niter) {
                 for (int k = 0; k < tpw; ++k) {
@@ -573,8 +582,19 @@ linear_train2_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restr
                 }
             }
         }
+        busy += BEAR_TRAIN_CLOCK() - t_it;
         __syncthreads();
     }
+#ifdef BEAR_TRAIN_EXPERIMENTS
+    if (lane == 0) {
+        atomicAdd(&g_train_cycles[producer ? 0 : 1], (unsigned long long)busy);
+        atomicAdd(&g_train_cycles[producer ? 3 : 4], 1ull);
+        if (threadIdx.x == 0) atomicAdd(&g_train_cycles[2], (unsigned long long)(clock64() - t_begin));
+    }
+#else
+    (void)busy;
+    (void)t_begin;
+#endif
 
     const int P = 2 + lag * A1 * A1;
     double* out = partials + int64_t(blockIdx.x) * P;
@@ -1116,6 +1136,17 @@ int launch_eval_nm(bool small, bool has_train, int grid, size_t smem, cudaStream
 }
 
 }  // namespace
+
+#ifdef BEAR_TRAIN_EXPERIMENTS
+// reads and clears the cycle counters of linear_train2_kernel (synchronises the device)
+extern "C" int bear_debug_train_cycles(unsigned long long* out5) {
+    BEAR_CUDA_CHECK(cudaDeviceSynchronize());
+    BEAR_CUDA_CHECK(cudaMemcpyFromSymbol(out5, g_train_cycles, 5 * sizeof(unsigned long long)));
+    const unsigned long long zero[5] = {0, 0, 0, 0, 0};
+    BEAR_CUDA_CHECK(cudaMemcpyToSymbol(g_train_cycles, zero, sizeof(zero)));
+    return BEAR_OK;
+}
+#endif
 
 extern "C" int64_t bear_workspace_doubles(int64_t n, int lag, int nparams) {
     (void)n;

@@ -228,15 +228,16 @@ def run_ours(args, rank, world_size, local_rank):
         torch.cuda.synchronize()
 
     w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    w0.record()
-    for _ in range(args.warmup):
+    for i in range(args.warmup):
+        if i == args.warmup - 1:
+            w0.record()                   # the last warm-up step alone: the first ones carry one-time costs (NCCL init)
         step()
     w1.record()
     barrier()
     # nvidia-smi answers in 0.1-0.3 s: when the K timed steps are shorter than ~1 s (small shards at N = 8) the same
     # step keeps running AFTER the timed region has been closed (s1 recorded) so that the sampler sees the clocks
     # under this load; the number of extra steps is the same on every rank (they contain the allreduce)
-    est = torch.tensor([w0.elapsed_time(w1) / max(args.warmup, 1)], dtype=torch.float64, device=dev)
+    est = torch.tensor([w0.elapsed_time(w1) if args.warmup > 0 else 1e9], dtype=torch.float64, device=dev)
     if world_size > 1:
         dist.all_reduce(est, op=dist.ReduceOp.MAX)
     est_ms = max(float(est), 1e-3)

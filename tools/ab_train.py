@@ -38,6 +38,16 @@ for lag, regime, name in ((20, 0, 'lag20'), (20, 2, 'lag20-sorted'), (13, 0, 'la
         for _ in range(2):
             fn()
         torch.cuda.synchronize()
+        cyc = None
+        if kn == 'train' and hasattr(lib, 'bear_debug_train_cycles'):      # built with -DBEAR_TRAIN_EXPERIMENTS
+            import ctypes
+            cyc = (ctypes.c_ulonglong * 5)()
+            lib.bear_debug_train_cycles(cyc)                                # clear
+            fn()
+            lib.bear_debug_train_cycles(cyc)
+            ctas = max(1, (cyc[3] + cyc[4]) // 16)
+            out.append('%s busy: producers %.2f, consumers %.2f of the kernel loop' % (
+                name, cyc[0] / max(1, cyc[2] * cyc[3] / ctas), cyc[1] / max(1, cyc[2] * cyc[4] / ctas)))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(5):
