@@ -259,3 +259,24 @@ def test_compact_transfer_format_is_lossless(alphabet, lag, n, monkeypatch):
             assert np.array_equal(k, table.kmers_host[r0:r0 + m])
             assert np.array_equal(c, table.counts_host[:, :, r0:r0 + m])
             assert esc.shape[0] == int((table.counts_host[:, :, r0:r0 + m] >= 255).sum())
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py --impl reference (the CPU arm: the oracle port on the host cores) prints exactly one line on stdout,
+    the JSON result with the contract's keys; under torchrun only rank 0 prints."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '1',
+           '--cpu-rows', '2048']
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, check=True).stdout
+    lines = [l for l in out.splitlines() if l.strip()]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    for key in ('impl', 'metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better',
+                'scaling', 'dtype', 'data', 'config', 'cpu_baseline', 'e2e'):
+        assert key in line, key
+    assert line['impl'] == 'reference' and line['cpu_baseline']['kind'] == 'port' and line['value'] > 0
+    env = dict(os.environ, RANK='1', WORLD_SIZE='2', LOCAL_RANK='1')
+    assert subprocess.run(cmd, capture_output=True, text=True, timeout=300, check=True, env=env).stdout.strip() == ''
