@@ -44,9 +44,10 @@ _SIGNATURES = {
     'bear_pack_sparse': (_i32, [_cp, _i32, _i32, _i32, _i64, _i64, _vp, _vp, _i64, _pi64, _pi32]),
     'bear_encode_kmers': (_i32, [_cp, _i64, _i32, _i32, _vp]),
     'bear_decode_kmers': (_i32, [_vp, _i64, _i32, _i32, _vp]),
-    'bear_compact_bytes': (_i64, [_i64, _i32, _i32, _i32]),
-    'bear_compact_table': (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _i64, _pi64]),
-    'bear_expand_table': (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _i64, _i64, _vp]),
+    'bear_compact_bytes': (_i64, [_i64, _i32, _i32, _i32, _i32]),
+    'bear_compact_choose_bits': (_i32, [_vp, _i64, _i64, _i64, _i32, _i32]),
+    'bear_compact_table': (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _pi64]),
+    'bear_expand_table': (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _i64, _vp]),
     'bear_decode_onehot': (_i32, [_vp, _i64, _i32, _i32, _vp, _vp]),
     'bear_decode_symbols': (_i32, [_vp, _i64, _i32, _i32, _vp, _vp]),
     'bear_unpack_counts': (_i32, [_vp, _i64, _i64, _i64, _i32, _i32, _vp, _vp]),

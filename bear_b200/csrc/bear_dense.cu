@@ -292,8 +292,8 @@ __global__ void synth_table_kernel(uint64_t* __restrict__ kmers, uint32_t* __res
 // plane, 128-bit stores of the count planes.
 // ---------------------------------------------------------------------------------------------
 __global__ void expand_table_kernel(const uint8_t* __restrict__ comp, int64_t pitch, int64_t n, int kb, int kbits_dna_lag,
-                                    int nplanes, uint64_t* __restrict__ kmers, uint32_t* __restrict__ counts,
-                                    int64_t stride, bool vec) {
+                                    int nplanes, int count_bits, uint64_t* __restrict__ kmers,
+                                    uint32_t* __restrict__ counts, int64_t stride, bool vec) {
     const int64_t q = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;       // rows 4q .. 4q+3
     const int64_t i0 = q * 4;
     if (i0 >= n) return;
@@ -311,15 +311,26 @@ __global__ void expand_table_kernel(const uint8_t* __restrict__ comp, int64_t pi
         }
         if (i0 + j < n) kmers[i0 + j] = v[j];
     }
+    const uint8_t* cplanes = comp + int64_t(kb) * pitch;
+    const int64_t cpitch = pitch * count_bits / 8;
     for (int pl = 0; pl < nplanes; ++pl) {
-        const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(comp + (int64_t(kb) + pl) * pitch) + q);
+        uint32_t c[4];
+        if (count_bits == 4) {          // two rows per byte, low nibble = even row: one 16-bit load per four rows
+            const uint32_t w = __ldg(reinterpret_cast<const uint16_t*>(cplanes + int64_t(pl) * cpitch) + q);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) c[j] = (w >> (4 * j)) & 0xfu;
+        } else {
+            const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(cplanes + int64_t(pl) * cpitch) + q);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) c[j] = (w >> (8 * j)) & 0xffu;
+        }
         uint32_t* dst = counts + int64_t(pl) * stride + i0;
         if (vec && i0 + 3 < n) {
-            *reinterpret_cast<uint4*>(dst) = make_uint4(w & 0xffu, (w >> 8) & 0xffu, (w >> 16) & 0xffu, w >> 24);
+            *reinterpret_cast<uint4*>(dst) = make_uint4(c[0], c[1], c[2], c[3]);
         } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-                if (i0 + j < n) dst[j] = (w >> (8 * j)) & 0xffu;
+                if (i0 + j < n) dst[j] = c[j];
         }
     }
 }
@@ -451,11 +462,11 @@ extern "C" int bear_synth_table(uint64_t* d_kmers, uint32_t* d_counts, int64_t s
 }
 
 extern "C" int bear_expand_table(const uint8_t* d_compact, const uint32_t* d_esc, int64_t n_esc, int64_t n, int lag,
-                                 int alphabet, int G, uint64_t* d_kmers, uint32_t* d_counts, int64_t stride,
-                                 int64_t dst_row0, void* stream) {
+                                 int alphabet, int G, int count_bits, uint64_t* d_kmers, uint32_t* d_counts,
+                                 int64_t stride, int64_t dst_row0, void* stream) {
     const char* fn = "bear_expand_table";
     const int a = bear_alphabet_size(alphabet);
-    BEAR_REQUIRE(a > 0 && lag >= 1 && lag <= bear_max_lag(alphabet) && G >= 1, fn);
+    BEAR_REQUIRE(a > 0 && lag >= 1 && lag <= bear_max_lag(alphabet) && G >= 1 && (count_bits == 4 || count_bits == 8), fn);
     BEAR_REQUIRE(n >= 0 && n_esc >= 0 && dst_row0 >= 0 && stride >= dst_row0 + n, fn);
     if (n == 0) return BEAR_OK;
     BEAR_REQUIRE(d_compact && d_kmers && d_counts && (d_esc || n_esc == 0), fn);
@@ -465,7 +476,7 @@ extern "C" int bear_expand_table(const uint8_t* d_compact, const uint32_t* d_esc
     const int64_t quads = (n + 3) / 4;
     const bool vec = (dst_row0 & 3) == 0 && (stride & 3) == 0 && (reinterpret_cast<uintptr_t>(d_counts) & 15) == 0;
     expand_table_kernel<<<unsigned((quads + THREADS - 1) / THREADS), THREADS, 0, ST(stream)>>>(
-        d_compact, pitch, n, kb, dna ? lag : 0, G * (a + 1), d_kmers + dst_row0, d_counts + dst_row0, stride, vec);
+        d_compact, pitch, n, kb, dna ? lag : 0, G * (a + 1), count_bits, d_kmers + dst_row0, d_counts + dst_row0, stride, vec);
     BEAR_LAUNCH_CHECK("expand_table_kernel");
     if (n_esc > 0) {
         expand_escapes_kernel<<<unsigned((n_esc + THREADS - 1) / THREADS), THREADS, 0, ST(stream)>>>(d_esc, n_esc,

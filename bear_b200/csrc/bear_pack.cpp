@@ -454,21 +454,67 @@ extern "C" int bear_pack_sparse(const char* path, int header, int alphabet, int 
 static inline int compact_kbits(int lag, int alphabet) { return alphabet == BEAR_ALPHABET_PROT ? 5 * lag : 2 * lag + 6; }
 static inline int64_t compact_pitch(int64_t n) { return (n + 15) / 16 * 16; }
 
-extern "C" int64_t bear_compact_bytes(int64_t n, int lag, int alphabet, int G) {
+static int pack_threads(int64_t n) {
+    int nthreads = int(std::thread::hardware_concurrency());
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 16) nthreads = 16;
+    if (const char* e = getenv("BEAR_PACK_THREADS")) nthreads = atoi(e) > 0 ? atoi(e) : nthreads;
+    if (n < 65536) nthreads = 1;
+    return nthreads;
+}
+
+extern "C" int64_t bear_compact_bytes(int64_t n, int lag, int alphabet, int G, int count_bits) {
     const int a = bear_alphabet_size(alphabet);
     if (a <= 0 || n < 0 || lag < 1 || lag > bear_max_lag(alphabet) || G < 1) return -1;
+    if (count_bits != 4 && count_bits != 8) return -1;
     const int kb = (compact_kbits(lag, alphabet) + 7) / 8;
-    return compact_pitch(n) * (kb + int64_t(G) * (a + 1));
+    const int64_t pitch = compact_pitch(n);
+    return pitch * kb + (pitch * count_bits / 8) * int64_t(G) * (a + 1);
+}
+
+extern "C" int bear_compact_choose_bits(const uint32_t* h_counts, int64_t stride, int64_t row0, int64_t n, int alphabet,
+                                        int G) {
+    const char* fn = "bear_compact_choose_bits";
+    const int a = bear_alphabet_size(alphabet);
+    BEAR_REQUIRE(a > 0 && G >= 1 && n >= 0 && row0 >= 0 && stride >= row0 + n, fn);
+    if (n == 0) return 8;
+    BEAR_REQUIRE(h_counts != nullptr, fn);
+    const int nplanes = G * (a + 1);
+    const int nthreads = pack_threads(n);
+    std::vector<int64_t> big15(nthreads, 0), big255(nthreads, 0);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthreads; ++t) {
+        pool.emplace_back([&, t]() {
+            int64_t e15 = 0, e255 = 0;
+            for (int pl = t; pl < nplanes; pl += nthreads) {
+                const uint32_t* src = h_counts + int64_t(pl) * stride + row0;
+                for (int64_t i = 0; i < n; ++i) {
+                    e15 += src[i] >= 15u;
+                    e255 += src[i] >= 255u;
+                }
+            }
+            big15[t] = e15;
+            big255[t] = e255;
+        });
+    }
+    for (auto& th : pool) th.join();
+    int64_t e15 = 0, e255 = 0;
+    for (int t = 0; t < nthreads; ++t) {
+        e15 += big15[t];
+        e255 += big255[t];
+    }
+    const int64_t bytes8 = n * nplanes + 12 * e255, bytes4 = n * nplanes / 2 + 12 * e15;
+    return bytes4 < bytes8 ? 4 : 8;
 }
 
 extern "C" int bear_compact_table(const uint64_t* h_kmers, const uint32_t* h_counts, int64_t stride, int64_t row0,
-                                  int64_t n, int lag, int alphabet, int G, uint8_t* h_out, uint32_t* h_esc,
-                                  int64_t esc_cap, int64_t* n_esc_out) {
+                                  int64_t n, int lag, int alphabet, int G, int count_bits, uint8_t* h_out,
+                                  uint32_t* h_esc, int64_t esc_cap, int64_t* n_esc_out) {
     const char* fn = "bear_compact_table";
     const int a = bear_alphabet_size(alphabet);
     BEAR_REQUIRE(a > 0 && lag >= 1 && lag <= bear_max_lag(alphabet) && G >= 1, fn);
     BEAR_REQUIRE(n >= 0 && row0 >= 0 && stride >= row0 + n && n < (int64_t(1) << 32) && esc_cap >= 0, fn);
-    BEAR_REQUIRE(n_esc_out != nullptr, fn);
+    BEAR_REQUIRE(n_esc_out != nullptr && (count_bits == 4 || count_bits == 8), fn);
     *n_esc_out = 0;
     if (n == 0) return BEAR_OK;
     BEAR_REQUIRE(h_kmers && h_counts && h_out && (h_esc || esc_cap == 0), fn);
@@ -476,11 +522,9 @@ extern "C" int bear_compact_table(const uint64_t* h_kmers, const uint32_t* h_cou
     const int64_t pitch = compact_pitch(n);
     const bool dna = alphabet != BEAR_ALPHABET_PROT;
     const int nplanes = G * A1;
-    int nthreads = int(std::thread::hardware_concurrency());
-    if (nthreads < 1) nthreads = 1;
-    if (nthreads > 16) nthreads = 16;
-    if (const char* e = getenv("BEAR_PACK_THREADS")) nthreads = atoi(e) > 0 ? atoi(e) : nthreads;
-    if (n < 65536) nthreads = 1;
+    const int64_t cpitch = pitch * count_bits / 8;      // bytes per count plane
+    const uint32_t marker = count_bits == 4 ? 15u : 255u;
+    const int nthreads = pack_threads(n);
     // k-mer planes: rows split over threads
     {
         std::vector<std::thread> pool;
@@ -507,19 +551,21 @@ extern "C" int bear_compact_table(const uint64_t* h_kmers, const uint32_t* h_cou
             pool.emplace_back([&, t]() {
                 for (int pl = t; pl < nplanes; pl += nthreads) {
                     const uint32_t* src = h_counts + int64_t(pl) * stride + row0;
-                    uint8_t* dst = h_out + (int64_t(kb) + pl) * pitch;
+                    uint8_t* dst = h_out + int64_t(kb) * pitch + int64_t(pl) * cpitch;
+                    if (count_bits == 4) memset(dst, 0, size_t(cpitch));
                     for (int64_t i = 0; i < n; ++i) {
-                        const uint32_t c = src[i];
-                        if (c >= 255u) {
-                            dst[i] = 255;
+                        uint32_t c = src[i];
+                        if (c >= marker) {
                             esc[pl].push_back(uint32_t(pl));
                             esc[pl].push_back(uint32_t(i));
                             esc[pl].push_back(c);
-                        } else {
-                            dst[i] = uint8_t(c);
+                            c = marker;
                         }
+                        if (count_bits == 4) dst[i >> 1] |= uint8_t(c << (4 * (i & 1)));
+                        else dst[i] = uint8_t(c);
                     }
-                    for (int64_t i = n; i < pitch; ++i) dst[i] = 0;
+                    if (count_bits == 8)
+                        for (int64_t i = n; i < pitch; ++i) dst[i] = 0;
                 }
             });
         }

@@ -261,8 +261,8 @@ def run_ours(args, rank, world_size, local_rank):
     results = acc.cpu().tolist()
 
     # ---- e2e: the same step from HOST-resident (pinned) buffers, copies inside the timed region ----
-    # The host side holds the table in the library's compact transfer format (byte planes + escapes,
-    # include/bear_b200.h: 11 B per row here instead of 28 B); every step copies it H2D chunk by chunk on a copy
+    # The host side holds the table in the library's compact transfer format (k-mer byte planes, 4-bit count planes
+    # + escapes, include/bear_b200.h: 8.5 B per row here instead of 28 B); every step copies it H2D chunk by chunk on a copy
     # stream, expands each chunk on the device (bear_expand_table) and trains on it while the next chunk is in flight.
     import ctypes
     e_rows = min(args.e2e_rows, n)
@@ -279,13 +279,15 @@ def run_ours(args, rank, world_size, local_rank):
     chunks = []                       # (lo, rows, pinned compact bytes, device buffers, pinned escapes, device escapes, n_esc)
     for lo, hi in zip(bounds[:-1], bounds[1:]):
         m = hi - lo
-        nb = lib.bear_compact_bytes(m, LAG, 0, 1)
+        bits = lib.bear_compact_choose_bits(ptr(hc), e_stride, lo, m, 0, 1)      # 4 for this table's sparse counts
+        check(bits)
+        nb = lib.bear_compact_bytes(m, LAG, 0, 1, bits)
         hb = torch.empty(nb, dtype=torch.uint8).pin_memory()
         cap = 1 << 16
         while True:
             esc = np.empty((cap, 3), dtype=np.uint32)
             need = ctypes.c_int64(0)
-            check(lib.bear_compact_table(ptr(hk), ptr(hc), e_stride, lo, m, LAG, 0, 1, ctypes.c_void_p(hb.data_ptr()),
+            check(lib.bear_compact_table(ptr(hk), ptr(hc), e_stride, lo, m, LAG, 0, 1, bits, ctypes.c_void_p(hb.data_ptr()),
                                          ptr(esc), cap, ctypes.byref(need)))
             if need.value <= cap:
                 break
@@ -293,7 +295,7 @@ def run_ours(args, rank, world_size, local_rank):
         he = torch.from_numpy(esc[:need.value].view(np.int32).copy()).pin_memory() if need.value else None
         dbs = [torch.empty_like(hb, device=dev) for _ in range(2)]            # double-buffered on the device
         des = [torch.empty_like(he, device=dev) for _ in range(2)] if he is not None else [None, None]
-        chunks.append((lo, m, hb, dbs, he, des, int(need.value)))
+        chunks.append((lo, m, hb, dbs, he, des, int(need.value), bits))
     del hk, hc
     col_d = ctypes_ptr(dc)
     pending, state = {}, {'k': 0}
@@ -302,7 +304,7 @@ def run_ours(args, rank, world_size, local_rank):
         """H2D of one step's input (all chunks) into device buffer set `slot`, on the copy stream."""
         evs = []
         with torch.cuda.stream(copy_stream):
-            for lo, m, hb, dbs, he, des, ne in chunks:
+            for lo, m, hb, dbs, he, des, ne, bits in chunks:
                 dbs[slot].copy_(hb, non_blocking=True)
                 if he is not None:
                     des[slot].copy_(he, non_blocking=True)
@@ -321,10 +323,10 @@ def run_ours(args, rank, world_size, local_rank):
         events = pending.pop(slot)
         issue_copies(slot ^ 1)
         grad.zero_()
-        for (lo, m, hb, dbs, he, des, ne), ev in zip(chunks, events):
+        for (lo, m, hb, dbs, he, des, ne, bits), ev in zip(chunks, events):
             main.wait_event(ev)
-            check(lib.bear_expand_table(ptr(dbs[slot]), ptr(des[slot]), ne, m, LAG, 0, 1, ptr(dk), ptr(dc), e_stride, lo,
-                                        _lib.stream()))
+            check(lib.bear_expand_table(ptr(dbs[slot]), ptr(des[slot]), ne, m, LAG, 0, 1, bits, ptr(dk), ptr(dc), e_stride,
+                                        lo, _lib.stream()))
             check(lib.bear_linear_train_step(ptr(dk), col_d, e_stride, lo, m, LAG, ptr(flat_params[1:]),
                                              ptr(flat_params[:1]), scale, 0, ptr(grad), None, ptr(ws), _lib.stream()))
         if world_size > 1:
@@ -379,7 +381,8 @@ def run_ours(args, rank, world_size, local_rank):
                        % (args.steps, extra_steps)),
         'e2e': {'value': e2e_value, 'unit': 'k-mer transition rows/s', 'h2d_bytes_per_step': h2d,
                 'd2h_bytes_per_step': d2h, 'rows_per_gpu_per_step': e_rows,
-                'host_format': 'compact transfer format (byte planes + escapes), %.1f B/row' % (h2d / e_rows)},
+                'host_format': 'compact transfer format (k-mer byte planes, %d-bit count planes, escapes), %.1f B/row'
+                               % (chunks[0][7], h2d / e_rows)},
         'gpu_launches': args.steps * 6,       # timed region: train + reduce, adam + bump, eval + reduce per step
         'roofline': {'bound': 'hbm', 'kernel': 'linear_train2_kernel<false>', 'achieved': achieved, 'peak': peak,
                      'unit': 'GB/s', 'frac': achieved / peak, 'traffic': TRAIN_DRAM_BYTES_PER_ROW_NCU * n,

@@ -214,7 +214,7 @@ def test_multithreaded_pack_equals_single_thread(tmp_path, monkeypatch):
         dl.KmerTable.from_file(bad, 'dna', 2)
 
 
-def _decode_compact(buf, esc, n, lag, alphabet, G, A1):
+def _decode_compact(buf, esc, n, lag, alphabet, G, A1, bits=8):
     """numpy reader of the compact transfer format (include/bear_b200.h)."""
     kbits = 5 * lag if alphabet == 'prot' else 2 * lag + 6
     kb, pitch = (kbits + 7) // 8, (n + 15) // 16 * 16
@@ -225,17 +225,23 @@ def _decode_compact(buf, esc, n, lag, alphabet, G, A1):
     if alphabet != 'prot':
         pay = v & np.uint64((1 << (2 * lag)) - 1)
         v = pay | ((v >> np.uint64(2 * lag)) << np.uint64(58))
-    counts = np.stack([b[(kb + pl) * pitch:(kb + pl) * pitch + n].astype(np.uint32) for pl in range(G * A1)])
+    if bits == 8:
+        counts = np.stack([b[(kb + pl) * pitch:(kb + pl) * pitch + n].astype(np.uint32) for pl in range(G * A1)])
+    else:                               # two rows per byte, low nibble = even row
+        cp = pitch // 2
+        planes = [b[kb * pitch + pl * cp:kb * pitch + (pl + 1) * cp].astype(np.uint32) for pl in range(G * A1)]
+        counts = np.stack([np.stack([p & 15, p >> 4], axis=1).reshape(-1)[:n] for p in planes])
     for pl, row, val in esc.numpy().view(np.uint32).reshape(-1, 3):
-        assert counts[pl, row] == 255
+        assert counts[pl, row] == (255 if bits == 8 else 15)
         counts[pl, row] = val
     return v, counts.reshape(G, A1, n)
 
 
 @pytest.mark.parametrize('alphabet,lag,n', [('dna', 20, 1000), ('dna', 29, 77), ('dna', 1, 16), ('prot', 12, 333), ('rna', 5, 70000)])
 def test_compact_transfer_format_is_lossless(alphabet, lag, n, monkeypatch):
-    """Host side of the compact transfer format: byte planes + escapes decode back to the packed table bit for bit
-    (counts on both sides of 255, up to 2^32 - 1; start-padded k-mers; sub-ranges; threaded and single-threaded)."""
+    """Host side of the compact transfer format: k-mer byte planes, 8- or 4-bit count planes and escapes decode back to
+    the packed table bit for bit (counts on both sides of 15 and 255, up to 2^32 - 1; start-padded k-mers;
+    sub-ranges; threaded and single-threaded)."""
     from bear_b200 import dataloader as dl
     rng = np.random.default_rng(lag * 1000 + n)
     A1 = (20 if alphabet == 'prot' else 4) + 1
@@ -253,12 +259,18 @@ def test_compact_transfer_format_is_lossless(alphabet, lag, n, monkeypatch):
     for threads in ('1', '4'):
         monkeypatch.setenv('BEAR_PACK_THREADS', threads)
         for r0, m in ((0, n), (3, n - 7), (n // 2, 1)):
-            buf, esc = table.compact_chunk(r0, m)
-            assert buf.numel() == table.compact_bytes(m)
-            k, c = _decode_compact(buf, esc, m, lag, alphabet, G, A1)
-            assert np.array_equal(k, table.kmers_host[r0:r0 + m])
-            assert np.array_equal(c, table.counts_host[:, :, r0:r0 + m])
-            assert esc.shape[0] == int((table.counts_host[:, :, r0:r0 + m] >= 255).sum())
+            for bits in (8, 4):
+                buf, esc, got = table.compact_chunk(r0, m, count_bits=bits)
+                assert got == bits and buf.numel() == table.compact_bytes(m, bits)
+                k, c = _decode_compact(buf, esc, m, lag, alphabet, G, A1, bits)
+                assert np.array_equal(k, table.kmers_host[r0:r0 + m])
+                assert np.array_equal(c, table.counts_host[:, :, r0:r0 + m])
+                assert esc.shape[0] == int((table.counts_host[:, :, r0:r0 + m] >= (255 if bits == 8 else 15)).sum())
+            # the chooser takes the width with fewer bytes on the wire, escapes (12 B each) included
+            sub = table.counts_host[:, :, r0:r0 + m]
+            bytes8 = sub.size + 12 * int((sub >= 255).sum())
+            bytes4 = sub.size // 2 + 12 * int((sub >= 15).sum())
+            assert table.compact_chunk(r0, m)[2] == (4 if bytes4 < bytes8 else 8)
 
 
 def test_bench_reference_arm_prints_one_json_line():

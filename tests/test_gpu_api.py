@@ -321,15 +321,24 @@ def test_upload_through_compact_format_is_bit_exact(cuda, alphabet, lag, n):
     assert np.array_equal(c.cpu().numpy().view(np.uint32), table.counts_host)
     # expansion at an unaligned destination (scalar stores)
     m = min(n, 1001)
-    buf, esc = table.compact_chunk(n - m, m)
-    k2 = torch.zeros(m + 8, dtype=torch.int64, device=cuda)
-    c2 = torch.zeros((3, A1, m + 8), dtype=torch.int32, device=cuda)
-    dbuf, desc = buf.to(cuda), (esc.to(cuda) if esc.numel() else None)
-    check(lib.bear_expand_table(ptr(dbuf), ptr(desc), esc.shape[0], m, lag, _lib.ALPHABET_IDS[alphabet], 3, ptr(k2), ptr(c2),
-                                m + 8, 3, _lib.stream()))
-    assert np.array_equal(k2[3:3 + m].cpu().numpy().view(np.uint64), table.kmers_host[n - m:n])
-    assert np.array_equal(c2[:, :, 3:3 + m].cpu().numpy().view(np.uint32), table.counts_host[:, :, n - m:n])
-    assert int(c2[:, :, :3].abs().sum()) == 0 and int(c2[:, :, 3 + m:].abs().sum()) == 0
+    for bits in (8, 4):                 # 4-bit count planes: every count >= 15 travels as an escape
+        buf, esc, got_bits = table.compact_chunk(n - m, m, count_bits=bits)
+        assert got_bits == bits and buf.numel() == table.compact_bytes(m, bits)
+        k2 = torch.zeros(m + 8, dtype=torch.int64, device=cuda)
+        c2 = torch.zeros((3, A1, m + 8), dtype=torch.int32, device=cuda)
+        dbuf, desc = buf.to(cuda), (esc.to(cuda) if esc.numel() else None)
+        check(lib.bear_expand_table(ptr(dbuf), ptr(desc), esc.shape[0], m, lag, _lib.ALPHABET_IDS[alphabet], 3, bits,
+                                    ptr(k2), ptr(c2), m + 8, 3, _lib.stream()))
+        assert np.array_equal(k2[3:3 + m].cpu().numpy().view(np.uint64), table.kmers_host[n - m:n])
+        assert np.array_equal(c2[:, :, 3:3 + m].cpu().numpy().view(np.uint32), table.counts_host[:, :, n - m:n])
+        assert int(c2[:, :, :3].abs().sum()) == 0 and int(c2[:, :, 3 + m:].abs().sum()) == 0
+    # sparse counts (the benchmark regime) choose the 4-bit planes, and the upload through them is bit exact
+    small = rng.poisson(0.6, size=(n, 3, A1)) * (rng.random((n, 3, A1)) < 0.999) + 40 * (rng.random((n, 3, A1)) < 0.001)
+    sparse = dl.KmerTable.from_arrays((codes, lag), small, alphabet)
+    assert sparse.compact_chunk(0, n)[2] == 4 and table.compact_chunk(0, n)[2] == 8
+    k3, c3 = sparse.device_tensors()
+    assert np.array_equal(k3.cpu().numpy().view(np.uint64), sparse.kmers_host)
+    assert np.array_equal(c3.cpu().numpy().view(np.uint32), sparse.counts_host)
 
 
 def test_assemble_follows_the_counted_sequence(cuda, tmp_path):
