@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get('BEAR_B200_LIB') or os.path.join(_HERE, 'libbear_b200.
 MAX_MODELS = 8
 HEAD_NONE, HEAD_LINEAR, HEAD_EXPLICIT, HEAD_STOP = 0, 1, 2, 3
 ALPHABET_IDS = {'dna': 0, 'rna': 1, 'prot': 2}
+WIRE_START_ESC = 16               # include/bear_b200.h BEAR_WIRE_START_ESC
 
 
 class BearError(RuntimeError):
@@ -45,7 +46,7 @@ _SIGNATURES = {
     'bear_encode_kmers': (_i32, [_cp, _i64, _i32, _i32, _vp]),
     'bear_decode_kmers': (_i32, [_vp, _i64, _i32, _i32, _vp]),
     'bear_compact_bytes': (_i64, [_i64, _i32, _i32, _i32, _i32]),
-    'bear_compact_choose_bits': (_i32, [_vp, _i64, _i64, _i64, _i32, _i32]),
+    'bear_compact_choose_wire': (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _i32, _i32]),
     'bear_compact_table': (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _pi64]),
     'bear_expand_table': (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _i64, _vp]),
     'bear_decode_onehot': (_i32, [_vp, _i64, _i32, _i32, _vp, _vp]),

@@ -305,7 +305,7 @@ __global__ void expand_table_kernel(const uint8_t* __restrict__ comp, int64_t pi
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        if (kbits_dna_lag > 0) {        // DNA / RNA: n_start sits above the 2*lag payload bits
+        if (kbits_dna_lag > 0) {        // DNA / RNA: n_start sits above the 2*lag payload bits (absent when it travels as escapes)
             const uint64_t pay = v[j] & ((uint64_t(1) << (2 * kbits_dna_lag)) - 1);
             v[j] = pay | ((v[j] >> (2 * kbits_dna_lag)) << 58);
         }
@@ -335,11 +335,13 @@ __global__ void expand_table_kernel(const uint8_t* __restrict__ comp, int64_t pi
     }
 }
 
-__global__ void expand_escapes_kernel(const uint32_t* __restrict__ esc, int64_t n_esc, uint32_t* __restrict__ counts,
-                                      int64_t stride) {
+__global__ void expand_escapes_kernel(const uint32_t* __restrict__ esc, int64_t n_esc, uint64_t* __restrict__ kmers,
+                                      uint32_t* __restrict__ counts, int64_t stride) {
     const int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (e >= n_esc) return;
-    counts[int64_t(esc[3 * e]) * stride + esc[3 * e + 1]] = esc[3 * e + 2];
+    const uint32_t plane = esc[3 * e], row = esc[3 * e + 1], val = esc[3 * e + 2];
+    if (plane == 0xffffffffu) kmers[row] |= uint64_t(val) << 58;        // n_start of a start-padded row
+    else counts[int64_t(plane) * stride + row] = val;
 }
 
 }  // namespace
@@ -462,16 +464,19 @@ extern "C" int bear_synth_table(uint64_t* d_kmers, uint32_t* d_counts, int64_t s
 }
 
 extern "C" int bear_expand_table(const uint8_t* d_compact, const uint32_t* d_esc, int64_t n_esc, int64_t n, int lag,
-                                 int alphabet, int G, int count_bits, uint64_t* d_kmers, uint32_t* d_counts,
+                                 int alphabet, int G, int wire, uint64_t* d_kmers, uint32_t* d_counts,
                                  int64_t stride, int64_t dst_row0, void* stream) {
     const char* fn = "bear_expand_table";
     const int a = bear_alphabet_size(alphabet);
+    const int count_bits = wire & 15;
+    const bool start_esc = (wire & BEAR_WIRE_START_ESC) != 0;
     BEAR_REQUIRE(a > 0 && lag >= 1 && lag <= bear_max_lag(alphabet) && G >= 1 && (count_bits == 4 || count_bits == 8), fn);
+    BEAR_REQUIRE((wire & ~(15 | BEAR_WIRE_START_ESC)) == 0 && !(start_esc && alphabet == BEAR_ALPHABET_PROT), fn);
     BEAR_REQUIRE(n >= 0 && n_esc >= 0 && dst_row0 >= 0 && stride >= dst_row0 + n, fn);
     if (n == 0) return BEAR_OK;
     BEAR_REQUIRE(d_compact && d_kmers && d_counts && (d_esc || n_esc == 0), fn);
     const bool dna = alphabet != BEAR_ALPHABET_PROT;
-    const int kb = ((dna ? 2 * lag + 6 : 5 * lag) + 7) / 8;
+    const int kb = ((dna ? 2 * lag + (start_esc ? 0 : 6) : 5 * lag) + 7) / 8;
     const int64_t pitch = (n + 15) / 16 * 16;
     const int64_t quads = (n + 3) / 4;
     const bool vec = (dst_row0 & 3) == 0 && (stride & 3) == 0 && (reinterpret_cast<uintptr_t>(d_counts) & 15) == 0;
@@ -479,8 +484,8 @@ extern "C" int bear_expand_table(const uint8_t* d_compact, const uint32_t* d_esc
         d_compact, pitch, n, kb, dna ? lag : 0, G * (a + 1), count_bits, d_kmers + dst_row0, d_counts + dst_row0, stride, vec);
     BEAR_LAUNCH_CHECK("expand_table_kernel");
     if (n_esc > 0) {
-        expand_escapes_kernel<<<unsigned((n_esc + THREADS - 1) / THREADS), THREADS, 0, ST(stream)>>>(d_esc, n_esc,
-                                                                                                  d_counts + dst_row0, stride);
+        expand_escapes_kernel<<<unsigned((n_esc + THREADS - 1) / THREADS), THREADS, 0, ST(stream)>>>(
+            d_esc, n_esc, d_kmers + dst_row0, d_counts + dst_row0, stride);
         BEAR_LAUNCH_CHECK("expand_escapes_kernel");
     }
     return BEAR_OK;

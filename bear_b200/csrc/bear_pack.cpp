@@ -451,7 +451,16 @@ extern "C" int bear_pack_sparse(const char* path, int header, int alphabet, int 
 // ------------------------------------------------------------------------------------------------
 // compact transfer format (see include/bear_b200.h)
 // ------------------------------------------------------------------------------------------------
-static inline int compact_kbits(int lag, int alphabet) { return alphabet == BEAR_ALPHABET_PROT ? 5 * lag : 2 * lag + 6; }
+static inline int compact_kbits(int lag, int alphabet, int wire = 0) {
+    if (alphabet == BEAR_ALPHABET_PROT) return 5 * lag;
+    return (wire & BEAR_WIRE_START_ESC) ? 2 * lag : 2 * lag + 6;
+}
+static inline bool wire_ok(int wire, int alphabet) {
+    const int bits = wire & 15;
+    if (bits != 4 && bits != 8) return false;
+    if (wire & ~(15 | BEAR_WIRE_START_ESC)) return false;
+    return !(wire & BEAR_WIRE_START_ESC) || alphabet != BEAR_ALPHABET_PROT;
+}
 static inline int64_t compact_pitch(int64_t n) { return (n + 15) / 16 * 16; }
 
 static int pack_threads(int64_t n) {
@@ -463,22 +472,23 @@ static int pack_threads(int64_t n) {
     return nthreads;
 }
 
-extern "C" int64_t bear_compact_bytes(int64_t n, int lag, int alphabet, int G, int count_bits) {
+extern "C" int64_t bear_compact_bytes(int64_t n, int lag, int alphabet, int G, int wire) {
     const int a = bear_alphabet_size(alphabet);
     if (a <= 0 || n < 0 || lag < 1 || lag > bear_max_lag(alphabet) || G < 1) return -1;
-    if (count_bits != 4 && count_bits != 8) return -1;
-    const int kb = (compact_kbits(lag, alphabet) + 7) / 8;
+    if (!wire_ok(wire, alphabet)) return -1;
+    const int kb = (compact_kbits(lag, alphabet, wire) + 7) / 8;
     const int64_t pitch = compact_pitch(n);
-    return pitch * kb + (pitch * count_bits / 8) * int64_t(G) * (a + 1);
+    return pitch * kb + (pitch * (wire & 15) / 8) * int64_t(G) * (a + 1);
 }
 
-extern "C" int bear_compact_choose_bits(const uint32_t* h_counts, int64_t stride, int64_t row0, int64_t n, int alphabet,
-                                        int G) {
-    const char* fn = "bear_compact_choose_bits";
+extern "C" int bear_compact_choose_wire(const uint64_t* h_kmers, const uint32_t* h_counts, int64_t stride, int64_t row0,
+                                        int64_t n, int lag, int alphabet, int G) {
+    const char* fn = "bear_compact_choose_wire";
     const int a = bear_alphabet_size(alphabet);
     BEAR_REQUIRE(a > 0 && G >= 1 && n >= 0 && row0 >= 0 && stride >= row0 + n, fn);
+    BEAR_REQUIRE(lag >= 1 && lag <= bear_max_lag(alphabet), fn);
     if (n == 0) return 8;
-    BEAR_REQUIRE(h_counts != nullptr, fn);
+    BEAR_REQUIRE(h_counts != nullptr && h_kmers != nullptr, fn);
     const int nplanes = G * (a + 1);
     const int nthreads = pack_threads(n);
     std::vector<int64_t> big15(nthreads, 0), big255(nthreads, 0);
@@ -504,28 +514,41 @@ extern "C" int bear_compact_choose_bits(const uint32_t* h_counts, int64_t stride
         e255 += big255[t];
     }
     const int64_t bytes8 = n * nplanes + 12 * e255, bytes4 = n * nplanes / 2 + 12 * e15;
-    return bytes4 < bytes8 ? 4 : 8;
+    int wire = bytes4 < bytes8 ? 4 : 8;
+    // start-run lengths as escapes: pays when it saves a k-mer plane and few rows are start-padded
+    if (alphabet != BEAR_ALPHABET_PROT) {
+        const int planes_saved = (compact_kbits(lag, alphabet, 0) + 7) / 8 - (compact_kbits(lag, alphabet, BEAR_WIRE_START_ESC) + 7) / 8;
+        if (planes_saved > 0) {
+            int64_t padded = 0;
+            for (int64_t i = 0; i < n; ++i) padded += (h_kmers[row0 + i] >> 58) != 0;
+            if (12 * padded < n * planes_saved) wire |= BEAR_WIRE_START_ESC;
+        }
+    }
+    return wire;
 }
 
 extern "C" int bear_compact_table(const uint64_t* h_kmers, const uint32_t* h_counts, int64_t stride, int64_t row0,
-                                  int64_t n, int lag, int alphabet, int G, int count_bits, uint8_t* h_out,
+                                  int64_t n, int lag, int alphabet, int G, int wire, uint8_t* h_out,
                                   uint32_t* h_esc, int64_t esc_cap, int64_t* n_esc_out) {
     const char* fn = "bear_compact_table";
     const int a = bear_alphabet_size(alphabet);
     BEAR_REQUIRE(a > 0 && lag >= 1 && lag <= bear_max_lag(alphabet) && G >= 1, fn);
     BEAR_REQUIRE(n >= 0 && row0 >= 0 && stride >= row0 + n && n < (int64_t(1) << 32) && esc_cap >= 0, fn);
-    BEAR_REQUIRE(n_esc_out != nullptr && (count_bits == 4 || count_bits == 8), fn);
+    BEAR_REQUIRE(n_esc_out != nullptr && wire_ok(wire, alphabet), fn);
+    const int count_bits = wire & 15;
+    const bool start_esc = (wire & BEAR_WIRE_START_ESC) != 0;
     *n_esc_out = 0;
     if (n == 0) return BEAR_OK;
     BEAR_REQUIRE(h_kmers && h_counts && h_out && (h_esc || esc_cap == 0), fn);
-    const int A1 = a + 1, kb = (compact_kbits(lag, alphabet) + 7) / 8;
+    const int A1 = a + 1, kb = (compact_kbits(lag, alphabet, wire) + 7) / 8;
     const int64_t pitch = compact_pitch(n);
     const bool dna = alphabet != BEAR_ALPHABET_PROT;
     const int nplanes = G * A1;
     const int64_t cpitch = pitch * count_bits / 8;      // bytes per count plane
     const uint32_t marker = count_bits == 4 ? 15u : 255u;
     const int nthreads = pack_threads(n);
-    // k-mer planes: rows split over threads
+    // k-mer planes: rows split over threads (start-run escapes per thread, i.e. ordered by row)
+    std::vector<std::vector<uint32_t>> kesc(nthreads);
     {
         std::vector<std::thread> pool;
         for (int t = 0; t < nthreads; ++t) {
@@ -533,7 +556,16 @@ extern "C" int bear_compact_table(const uint64_t* h_kmers, const uint32_t* h_cou
                 const int64_t lo = n * t / nthreads, hi = n * (t + 1) / nthreads;
                 for (int64_t i = lo; i < hi; ++i) {
                     const uint64_t code = h_kmers[row0 + i];
-                    const uint64_t v = dna ? ((code & ((uint64_t(1) << 58) - 1)) | ((code >> 58) << (2 * lag))) : code;
+                    uint64_t v = code;
+                    if (dna) {
+                        const uint64_t pay = code & ((uint64_t(1) << 58) - 1), ns = code >> 58;
+                        v = start_esc ? pay : (pay | (ns << (2 * lag)));
+                        if (start_esc && ns != 0) {
+                            kesc[t].push_back(0xffffffffu);
+                            kesc[t].push_back(uint32_t(i));
+                            kesc[t].push_back(uint32_t(ns));
+                        }
+                    }
                     for (int b = 0; b < kb; ++b) h_out[int64_t(b) * pitch + i] = uint8_t(v >> (8 * b));
                 }
                 for (int b = 0; b < kb; ++b)
@@ -573,12 +605,17 @@ extern "C" int bear_compact_table(const uint64_t* h_kmers, const uint32_t* h_cou
     }
     int64_t total = 0;
     for (int pl = 0; pl < nplanes; ++pl) total += int64_t(esc[pl].size() / 3);
+    for (int t = 0; t < nthreads; ++t) total += int64_t(kesc[t].size() / 3);
     *n_esc_out = total;
     if (total > esc_cap) return BEAR_OK;              // caller re-calls with room for *n_esc_out entries
     int64_t o = 0;
     for (int pl = 0; pl < nplanes; ++pl) {
         if (!esc[pl].empty()) memcpy(h_esc + o * 3, esc[pl].data(), esc[pl].size() * sizeof(uint32_t));
         o += int64_t(esc[pl].size() / 3);
+    }
+    for (int t = 0; t < nthreads; ++t) {                 // start-run lengths after the count escapes
+        if (!kesc[t].empty()) memcpy(h_esc + o * 3, kesc[t].data(), kesc[t].size() * sizeof(uint32_t));
+        o += int64_t(kesc[t].size() / 3);
     }
     return BEAR_OK;
 }

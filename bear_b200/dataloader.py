@@ -185,17 +185,18 @@ class KmerTable:
         return KmerTable(kmers, counts, K, self.lag, self.alphabet)
 
     # -- device residency ---------------------------------------------------------------------
-    def compact_chunk(self, r0, n, out=None, count_bits=None):
+    def compact_chunk(self, r0, n, out=None, wire=None):
         """Rows [r0, r0+n) in the compact transfer format (k-mer byte planes, 8- or 4-bit count planes + escapes for
-        the counts that do not fit, see include/bear_b200.h): (uint8 tensor, uint32 escape tensor [n_esc, 3],
-        count_bits).  ``count_bits`` None: the width with fewer bytes on the wire for these rows
-        (bear_compact_choose_bits).  ``out`` = a reusable (pinned) uint8 tensor of at least ``compact_bytes(n)``
-        elements."""
+        what does not fit, see include/bear_b200.h): (uint8 tensor, uint32 escape tensor [n_esc, 3], wire).
+        ``wire``: the variant (count bits, + _lib.WIRE_START_ESC); None = the one with the fewest bytes on the wire
+        for these rows (bear_compact_choose_wire).  ``out`` = a reusable (pinned) uint8 tensor of at least
+        ``compact_bytes(n)`` elements."""
         aid = _lib.ALPHABET_IDS[self.alphabet]
-        if count_bits is None:
-            count_bits = lib.bear_compact_choose_bits(ptr(self.counts_host), self.stride, r0, n, aid, self.num_ds)
-            check(count_bits)
-        nbytes = lib.bear_compact_bytes(n, self.lag, aid, self.num_ds, count_bits)
+        if wire is None:
+            wire = lib.bear_compact_choose_wire(ptr(self.kmers_host), ptr(self.counts_host), self.stride, r0, n,
+                                                self.lag, aid, self.num_ds)
+            check(wire)
+        nbytes = lib.bear_compact_bytes(n, self.lag, aid, self.num_ds, wire)
         check(nbytes)
         buf = out[:nbytes] if out is not None else torch.empty(nbytes, dtype=torch.uint8)
         cap = 1024
@@ -203,19 +204,19 @@ class KmerTable:
             esc = np.empty((cap, 3), dtype=np.uint32)
             need = ctypes.c_int64(0)
             check(lib.bear_compact_table(ptr(self.kmers_host), ptr(self.counts_host), self.stride, r0, n, self.lag, aid,
-                                         self.num_ds, count_bits, ctypes.c_void_p(buf.data_ptr()), ptr(esc), cap,
+                                         self.num_ds, wire, ctypes.c_void_p(buf.data_ptr()), ptr(esc), cap,
                                          ctypes.byref(need)))
             if need.value <= cap:
-                return buf, torch.from_numpy(esc[:need.value].view(np.int32).copy()), count_bits
+                return buf, torch.from_numpy(esc[:need.value].view(np.int32).copy()), wire
             cap = int(need.value)
 
-    def compact_bytes(self, n, count_bits=8):
-        return int(lib.bear_compact_bytes(n, self.lag, _lib.ALPHABET_IDS[self.alphabet], self.num_ds, count_bits))
+    def compact_bytes(self, n, wire=8):
+        return int(lib.bear_compact_bytes(n, self.lag, _lib.ALPHABET_IDS[self.alphabet], self.num_ds, wire))
 
     def device_tensors(self):
         """(kmers int64 [stride], counts int32 [G, A1, stride]) on the current CUDA device; the bit
         patterns are the uint64 / uint32 of the packed layout.  The upload crosses the bus in the compact transfer
-        format (8.5 - 11 instead of 28 bytes per row for a one-column DNA table at lag 20) through a bounded pinned
+        format (7.6 - 11 instead of 28 bytes per row for a one-column DNA table at lag 20) through a bounded pinned
         buffer and is expanded on the device (bear_expand_table), bit-exactly."""
         if self._dev is None:
             dev = _lib.device()

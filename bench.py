@@ -262,7 +262,7 @@ def run_ours(args, rank, world_size, local_rank):
 
     # ---- e2e: the same step from HOST-resident (pinned) buffers, copies inside the timed region ----
     # The host side holds the table in the library's compact transfer format (k-mer byte planes, 4-bit count planes
-    # + escapes, include/bear_b200.h: 8.5 B per row here instead of 28 B); every step copies it H2D chunk by chunk on a copy
+    # + escapes, include/bear_b200.h: 7.6 B per row here instead of 28 B); every step copies it H2D chunk by chunk on a copy
     # stream, expands each chunk on the device (bear_expand_table) and trains on it while the next chunk is in flight.
     import ctypes
     e_rows = min(args.e2e_rows, n)
@@ -279,7 +279,7 @@ def run_ours(args, rank, world_size, local_rank):
     chunks = []                       # (lo, rows, pinned compact bytes, device buffers, pinned escapes, device escapes, n_esc)
     for lo, hi in zip(bounds[:-1], bounds[1:]):
         m = hi - lo
-        bits = lib.bear_compact_choose_bits(ptr(hc), e_stride, lo, m, 0, 1)      # 4 for this table's sparse counts
+        bits = lib.bear_compact_choose_wire(ptr(hk), ptr(hc), e_stride, lo, m, LAG, 0, 1)   # 4-bit counts, start runs as escapes
         check(bits)
         nb = lib.bear_compact_bytes(m, LAG, 0, 1, bits)
         hb = torch.empty(nb, dtype=torch.uint8).pin_memory()
@@ -381,8 +381,8 @@ def run_ours(args, rank, world_size, local_rank):
                        % (args.steps, extra_steps)),
         'e2e': {'value': e2e_value, 'unit': 'k-mer transition rows/s', 'h2d_bytes_per_step': h2d,
                 'd2h_bytes_per_step': d2h, 'rows_per_gpu_per_step': e_rows,
-                'host_format': 'compact transfer format (k-mer byte planes, %d-bit count planes, escapes), %.1f B/row'
-                               % (chunks[0][7], h2d / e_rows)},
+                'host_format': 'compact transfer format (k-mer byte planes, %d-bit count planes, escapes%s), %.1f B/row'
+                               % (chunks[0][7] & 15, ' incl. start-run lengths' if chunks[0][7] & 16 else '', h2d / e_rows)},
         'gpu_launches': args.steps * 6,       # timed region: train + reduce, adam + bump, eval + reduce per step
         'roofline': {'bound': 'hbm', 'kernel': 'linear_train2_kernel<false>', 'achieved': achieved, 'peak': peak,
                      'unit': 'GB/s', 'frac': achieved / peak, 'traffic': TRAIN_DRAM_BYTES_PER_ROW_NCU * n,

@@ -94,25 +94,29 @@ int bear_decode_kmers(const uint64_t* h_kmers, int64_t n, int lag, int alphabet,
  * table can cross the bus as byte planes: ceil(kbits/8) planes for the k-mer (kbits = 2*lag + 6 for DNA/RNA --
  * the 6 bits hold n_start --, 5*lag for protein) and one byte plane per count column and letter; a count
  * >= 255 is stored as 255 plus an escape entry {plane, row, value}.  Lossless for any table.
- * count_bits = 4 halves the count planes (two rows per byte, low nibble = even row; a count >= 15 is stored as 15
- * plus an escape): 8.5 instead of 11 B per row for a one-column DNA table at lag 20 with sparse counts.
- * bear_compact_choose_bits (host) scans the counts of the rows and returns the width (4 or 8) with fewer bytes
- * on the wire, escapes (12 B each) included.
- * Plane pitch = n rounded up to 16 bytes (count planes: pitch * count_bits / 8); bear_compact_bytes() = the size
- * of all planes of n rows.
+ * `wire` selects the variant: wire & 15 = bits per count, 8 or 4 (4: two rows per byte, low nibble = even row; a
+ * count >= 15 is stored as 15 plus an escape); wire & BEAR_WIRE_START_ESC (DNA/RNA): the k-mer planes hold the 2*lag
+ * payload bits only and n_start of the start-padded rows travels as escape entries {0xffffffff, row, n_start} after
+ * the count escapes -- one plane less at lag 20.  7.6 instead of 11 B per row for a one-column DNA table at lag 20
+ * with sparse counts and 1 % start-padded rows.  bear_compact_choose_wire (host) scans the rows and returns the
+ * variant with the fewest bytes on the wire, escapes (12 B each) included.
+ * Plane pitch = n rounded up to 16 bytes (count planes: pitch * bits / 8); bear_compact_bytes() = the size of all
+ * planes of n rows.
  * bear_compact_table (host, multi-threaded) writes rows [row0, row0+n) of a packed table into h_out and the
  * escapes (sorted by plane, row) into h_esc[esc_cap][3]; *n_esc_out = entries needed (re-call with a larger
  * capacity if it exceeds esc_cap).  bear_expand_table (device) restores rows [dst_row0, dst_row0+n) of the packed
  * table d_kmers / d_counts (plane pitch `stride`) bit-exactly.  Replaces nothing in the reference (its loader
  * re-parses text every epoch, dataloader.py:36-46); it is the wire format of dataloader.KmerTable uploads.
  * ---------------------------------------------------------------------------------------- */
-int64_t bear_compact_bytes(int64_t n, int lag, int alphabet, int G, int count_bits);
-int bear_compact_choose_bits(const uint32_t* h_counts, int64_t stride, int64_t row0, int64_t n, int alphabet, int G);
+#define BEAR_WIRE_START_ESC 16
+int64_t bear_compact_bytes(int64_t n, int lag, int alphabet, int G, int wire);
+int bear_compact_choose_wire(const uint64_t* h_kmers, const uint32_t* h_counts, int64_t stride, int64_t row0, int64_t n,
+                             int lag, int alphabet, int G);
 int bear_compact_table(const uint64_t* h_kmers, const uint32_t* h_counts, int64_t stride, int64_t row0, int64_t n,
-                       int lag, int alphabet, int G, int count_bits, uint8_t* h_out, uint32_t* h_esc, int64_t esc_cap,
+                       int lag, int alphabet, int G, int wire, uint8_t* h_out, uint32_t* h_esc, int64_t esc_cap,
                        int64_t* n_esc_out);
 int bear_expand_table(const uint8_t* d_compact, const uint32_t* d_esc, int64_t n_esc, int64_t n, int lag,
-                      int alphabet, int G, int count_bits, uint64_t* d_kmers, uint32_t* d_counts, int64_t stride,
+                      int alphabet, int G, int wire, uint64_t* d_kmers, uint32_t* d_counts, int64_t stride,
                       int64_t dst_row0, void* stream);
 
 /* ------------------------------------------------------------------------------------------

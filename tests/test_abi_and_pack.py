@@ -214,9 +214,10 @@ def test_multithreaded_pack_equals_single_thread(tmp_path, monkeypatch):
         dl.KmerTable.from_file(bad, 'dna', 2)
 
 
-def _decode_compact(buf, esc, n, lag, alphabet, G, A1, bits=8):
+def _decode_compact(buf, esc, n, lag, alphabet, G, A1, wire=8):
     """numpy reader of the compact transfer format (include/bear_b200.h)."""
-    kbits = 5 * lag if alphabet == 'prot' else 2 * lag + 6
+    bits, start_esc = wire & 15, bool(wire & 16)
+    kbits = 5 * lag if alphabet == 'prot' else 2 * lag + (0 if start_esc else 6)
     kb, pitch = (kbits + 7) // 8, (n + 15) // 16 * 16
     b = buf.numpy()
     v = np.zeros(n, dtype=np.uint64)
@@ -232,6 +233,10 @@ def _decode_compact(buf, esc, n, lag, alphabet, G, A1, bits=8):
         planes = [b[kb * pitch + pl * cp:kb * pitch + (pl + 1) * cp].astype(np.uint32) for pl in range(G * A1)]
         counts = np.stack([np.stack([p & 15, p >> 4], axis=1).reshape(-1)[:n] for p in planes])
     for pl, row, val in esc.numpy().view(np.uint32).reshape(-1, 3):
+        if pl == 0xffffffff:            # n_start of a start-padded row
+            assert start_esc and v[row] >> np.uint64(58) == 0
+            v[row] |= np.uint64(val) << np.uint64(58)
+            continue
         assert counts[pl, row] == (255 if bits == 8 else 15)
         counts[pl, row] = val
     return v, counts.reshape(G, A1, n)
@@ -259,18 +264,24 @@ def test_compact_transfer_format_is_lossless(alphabet, lag, n, monkeypatch):
     for threads in ('1', '4'):
         monkeypatch.setenv('BEAR_PACK_THREADS', threads)
         for r0, m in ((0, n), (3, n - 7), (n // 2, 1)):
-            for bits in (8, 4):
-                buf, esc, got = table.compact_chunk(r0, m, count_bits=bits)
-                assert got == bits and buf.numel() == table.compact_bytes(m, bits)
-                k, c = _decode_compact(buf, esc, m, lag, alphabet, G, A1, bits)
-                assert np.array_equal(k, table.kmers_host[r0:r0 + m])
-                assert np.array_equal(c, table.counts_host[:, :, r0:r0 + m])
-                assert esc.shape[0] == int((table.counts_host[:, :, r0:r0 + m] >= (255 if bits == 8 else 15)).sum())
-            # the chooser takes the width with fewer bytes on the wire, escapes (12 B each) included
-            sub = table.counts_host[:, :, r0:r0 + m]
+            sub, ksub = table.counts_host[:, :, r0:r0 + m], table.kmers_host[r0:r0 + m]
+            padded = 0 if alphabet == 'prot' else int((ksub >> np.uint64(58) != 0).sum())
+            for wire in (8, 4) + (() if alphabet == 'prot' else (8 | 16, 4 | 16)):
+                buf, esc, got = table.compact_chunk(r0, m, wire=wire)
+                assert got == wire and buf.numel() == table.compact_bytes(m, wire)
+                k, c = _decode_compact(buf, esc, m, lag, alphabet, G, A1, wire)
+                assert np.array_equal(k, ksub)
+                assert np.array_equal(c, sub)
+                assert esc.shape[0] == int((sub >= (255 if wire & 15 == 8 else 15)).sum()) + (padded if wire & 16 else 0)
+            # the chooser takes the variant with the fewest bytes on the wire, escapes (12 B each) included
             bytes8 = sub.size + 12 * int((sub >= 255).sum())
             bytes4 = sub.size // 2 + 12 * int((sub >= 15).sum())
-            assert table.compact_chunk(r0, m)[2] == (4 if bytes4 < bytes8 else 8)
+            want = 4 if bytes4 < bytes8 else 8
+            if alphabet != 'prot':
+                saved = (2 * lag + 6 + 7) // 8 - (2 * lag + 7) // 8
+                if saved > 0 and 12 * padded < m * saved:
+                    want |= 16
+            assert table.compact_chunk(r0, m)[2] == want
 
 
 def test_bench_reference_arm_prints_one_json_line():

@@ -321,8 +321,9 @@ def test_upload_through_compact_format_is_bit_exact(cuda, alphabet, lag, n):
     assert np.array_equal(c.cpu().numpy().view(np.uint32), table.counts_host)
     # expansion at an unaligned destination (scalar stores)
     m = min(n, 1001)
-    for bits in (8, 4):                 # 4-bit count planes: every count >= 15 travels as an escape
-        buf, esc, got_bits = table.compact_chunk(n - m, m, count_bits=bits)
+    # 4-bit count planes: every count >= 15 travels as an escape; | 16: so do the start-run lengths (DNA / RNA)
+    for bits in (8, 4) + (() if alphabet == 'prot' else (8 | 16, 4 | 16)):
+        buf, esc, got_bits = table.compact_chunk(n - m, m, wire=bits)
         assert got_bits == bits and buf.numel() == table.compact_bytes(m, bits)
         k2 = torch.zeros(m + 8, dtype=torch.int64, device=cuda)
         c2 = torch.zeros((3, A1, m + 8), dtype=torch.int32, device=cuda)
@@ -335,7 +336,15 @@ def test_upload_through_compact_format_is_bit_exact(cuda, alphabet, lag, n):
     # sparse counts (the benchmark regime) choose the 4-bit planes, and the upload through them is bit exact
     small = rng.poisson(0.6, size=(n, 3, A1)) * (rng.random((n, 3, A1)) < 0.999) + 40 * (rng.random((n, 3, A1)) < 0.001)
     sparse = dl.KmerTable.from_arrays((codes, lag), small, alphabet)
-    assert sparse.compact_chunk(0, n)[2] == 4 and table.compact_chunk(0, n)[2] == 8
+    assert sparse.compact_chunk(0, n)[2] & 15 == 4 and table.compact_chunk(0, n)[2] & 15 == 8
+    if alphabet == 'dna' and lag == 20:     # 1 % start-padded rows: the start-run lengths travel as escapes, 5 k-mer planes
+        few = codes.copy()
+        few[100:] &= np.uint64((1 << 58) - 1)
+        t2 = dl.KmerTable.from_arrays((few, lag), small, alphabet)
+        assert t2.compact_chunk(0, n)[2] == 4 | 16
+        k4, c4 = t2.device_tensors()
+        assert np.array_equal(k4.cpu().numpy().view(np.uint64), t2.kmers_host)
+        assert np.array_equal(c4.cpu().numpy().view(np.uint32), t2.counts_host)
     k3, c3 = sparse.device_tensors()
     assert np.array_equal(k3.cpu().numpy().view(np.uint64), sparse.kmers_host)
     assert np.array_equal(c3.cpu().numpy().view(np.uint32), sparse.counts_host)
