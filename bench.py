@@ -413,8 +413,13 @@ def run_ours(args, rank, world_size, local_rank):
         dist.destroy_process_group()
 
 
-def print_result(line):          # replaced in main() by a writer on the saved stdout descriptor
-    print(line)
+_RESULT_OUT = None               # the process's original stdout, saved by main() before fd 1 is pointed at stderr
+
+
+def print_result(line):
+    out = _RESULT_OUT or sys.stdout
+    out.write(line + '\n')
+    out.flush()
 
 
 def ctypes_ptr(t):
@@ -426,15 +431,10 @@ def main():
     args = parse()
     # stdout carries exactly ONE line, the JSON result: libraries that print to file descriptor 1 (NCCL writes
     # "NCCL version ..." there on communicator creation) are sent to stderr for the rest of the run
+    global _RESULT_OUT
     sys.stdout.flush()
-    result_fd = os.dup(1)
+    _RESULT_OUT = os.fdopen(os.dup(1), 'w')
     os.dup2(2, 1)
-    global print_result
-    result_out = os.fdopen(result_fd, 'w')
-
-    def print_result(line):
-        result_out.write(line + '\n')
-        result_out.flush()
     rank = int(os.environ.get('RANK', 0))
     world_size = int(os.environ.get('WORLD_SIZE', 1))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
