@@ -182,14 +182,20 @@ int expect(Cur& c, char ch, const char* what) {
     return BEAR_ERR_PARSE;
 }
 
-// non-negative integer-valued JSON number -> uint32.  Plain digit strings take the fast path; anything
-// else (1.0, 3e0, -2, 2.5) goes through strtod on a bounded copy.
+// non-negative integer-valued JSON number -> uint32.  Digit strings, also with a ".0" / ".000" tail (what
+// json.dumps writes for float arrays), take the fast path; anything else (3e0, -2, 2.5) goes through strtod on a
+// bounded copy.
 int parse_count(Cur& c, uint32_t* out, const char* what) {
     c.ws();
     const char* s = c.p;
     uint64_t v = 0;
     int nd = 0;
     while (s < c.e && *s >= '0' && *s <= '9' && nd < 11) { v = v * 10 + uint64_t(*s - '0'); ++s; ++nd; }
+    if (nd > 0 && nd < 11 && s < c.e && *s == '.') {          // "12.0", "12.": skip a tail of zeros
+        const char* z = s + 1;
+        while (z < c.e && *z == '0') ++z;
+        if (z == c.e || !((*z >= '1' && *z <= '9') || *z == 'e' || *z == 'E')) s = z;
+    }
     if (nd > 0 && nd < 11 && (s == c.e || (*s != '.' && *s != 'e' && *s != 'E'))) {
         if (v > 4294967295ull) { bear_set_error("count %llu in %s exceeds uint32", (unsigned long long)v, what); return BEAR_ERR_RANGE; }
         *out = uint32_t(v);

@@ -145,6 +145,13 @@ def test_pack_edge_inputs(tmp_path):
     assert int(t.kmers_host[1] >> np.uint64(58)) == 3
     ds = dl.KmerDataset(t, 1).repeat(3)
     assert len(ds) == 6 and [b[:2] for b in ds.batches()] == [(0, 1), (1, 1)] * 3
+    # integer-valued decimals (json.dumps of float arrays) take the packer's fast path; a fractional part is an error
+    text = 'ACGT\t[[5.000, 7., 12.0, 4294967295.0, 1.0e1]]\nTTTT\t[[0.0, 0.00 , 3.0,1.0 ,2]]\n'
+    t = dl.KmerTable.from_file(_write(tmp_path, text, 'dec.tsv'), 'dna', 1)
+    assert t.counts_host[0, :, 0].tolist() == [5, 7, 12, 4294967295, 10] and t.counts_host[0, :, 1].tolist() == [0, 0, 3, 1, 2]
+    for bad in ('ACGT\t[[1.05,0,0,0,0]]\n', 'ACGT\t[[1.0.0,0,0,0,0]]\n', 'ACGT\t[[4294967296.0,0,0,0,0]]\n'):
+        with pytest.raises(Exception):
+            dl.KmerTable.from_file(_write(tmp_path, bad, 'bad_dec.tsv'), 'dna', 1)
 
 
 def test_dataset_batching_and_sharding_cover_every_row_once():
