@@ -73,6 +73,35 @@ static int encode_one(const char* s, int lag, int alphabet, uint64_t* out) {
         *out = v;
         return 0;
     }
+    {   // common case: a run of '[' followed by letters only -- one table look-up per symbol
+        static const struct Lut {
+            int8_t t[2][256];
+            Lut() {
+                memset(t, -1, sizeof(t));
+                for (int a = 0; a < 2; ++a) {
+                    t[a][int('A')] = 0;
+                    t[a][int('C')] = 1;
+                    t[a][int('G')] = 2;
+                    t[a][int(a == 0 ? 'T' : 'U')] = 3;
+                }
+            }
+        } lut;
+        const int8_t* t = lut.t[alphabet == BEAR_ALPHABET_DNA ? 0 : 1];
+        int j = 0;
+        while (j < lag && s[j] == '[') ++j;
+        const uint64_t ns = uint64_t(j);
+        uint64_t w = 0;
+        int bad = 0;
+        for (; j < lag; ++j) {
+            const int c = t[uint8_t(s[j])];
+            bad |= c;
+            w = (w << 2) | uint64_t(c & 3);
+        }
+        if (bad >= 0) {
+            *out = w | (ns << 58);
+            return 0;
+        }
+    }   // otherwise: the general loop below finds and reports the offending symbol
     uint64_t v = 0, nstart = 0;
     bool in_prefix = true;
     for (int j = 0; j < lag; ++j) {
@@ -232,11 +261,47 @@ int check_kmer(const PackJob& j, const char* s, int len, int64_t file_row, uint6
     return encode_one(s, len, j.alphabet, out);
 }
 
+// The usual shape of a count matrix, "[[1,2,3,4,5],[...]]" with optional blanks and integer-valued decimals
+// ("1.0"), parsed without the generic cursor; false = something else was met (nothing is reported: the caller
+// re-parses the line with the generic routine, which either succeeds or names the error).
+bool fast_tsv_counts(const PackJob& j, const char* p, const char* e, int64_t out_row) {
+#define BEAR_SKIP_BLANKS() while (p < e && *p == ' ') ++p
+#define BEAR_NEED(ch) do { BEAR_SKIP_BLANKS(); if (p >= e || *p != (ch)) return false; ++p; } while (0)
+    BEAR_NEED('[');
+    for (int g = 0; g < j.num_ds; ++g) {
+        if (g) BEAR_NEED(',');
+        BEAR_NEED('[');
+        for (int a = 0; a < j.A1; ++a) {
+            if (a) BEAR_NEED(',');
+            BEAR_SKIP_BLANKS();
+            uint32_t v = 0;
+            int nd = 0;
+            while (p < e && unsigned(*p - '0') < 10u && nd < 10) { v = v * 10u + uint32_t(*p - '0'); ++p; ++nd; }
+            if (nd == 0 || nd > 9) return false;                       // up to 9 digits: below 2^32
+            if (p < e && *p == '.') {                                    // "12.0", "12."
+                const char* z = p + 1;
+                while (z < e && *z == '0') ++z;
+                if (z < e && ((*z >= '1' && *z <= '9') || *z == 'e' || *z == 'E' || *z == '.')) return false;
+                p = z;
+            } else if (p < e && (*p == 'e' || *p == 'E')) {
+                return false;
+            }
+            j.counts[(int64_t(g) * j.A1 + a) * j.stride + out_row] = v;
+        }
+        BEAR_NEED(']');
+    }
+    BEAR_NEED(']');
+#undef BEAR_NEED
+#undef BEAR_SKIP_BLANKS
+    return true;
+}
+
 int parse_tsv_line(const PackJob& j, const char* b, const char* e, int64_t file_row, int64_t out_row) {
     const char* tab = static_cast<const char*>(memchr(b, '\t', size_t(e - b)));
     if (!tab) { bear_set_error("row %lld: no tab separator", (long long)(file_row + 1)); return BEAR_ERR_PARSE; }
     int rc = check_kmer(j, b, int(tab - b), file_row, j.kmers + out_row);
     if (rc) return rc;
+    if (fast_tsv_counts(j, tab + 1, e, out_row)) return 0;
     Cur c{tab + 1, e};
     if ((rc = expect(c, '[', "count matrix"))) return rc;
     for (int g = 0; g < j.num_ds; ++g) {
