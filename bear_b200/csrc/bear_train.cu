@@ -1,0 +1,500 @@
+// Fused training step of the linear-head BEAR model on a packed DNA/RNA table (A1 = 5):
+//   bear_net._train_step (bear_net.py:146-197) + ar_funcs.make_ar_func_linear (ar_funcs.py:23-46)
+//   + core.*.counts_log_prob (core.py:73-74,138-139), forward and analytic backward in ONE pass over the table.
+//
+// linear_train_tc_kernel: one persistent CTA of 16 warps per SM.
+//   * Warps 0..14 are independent row pipelines.  Each owns a ring of shared-memory stages that lane 0 fills with 1-D bulk
+//     async copies (TMA: the k-mer plane and the five count planes of a 32-row tile, 896 bytes, completion on an mbarrier);
+//     the warp decodes the tile, evaluates the head as a product of chunk-table rows, the Dirichlet-multinomial (or
+//     multinomial) log-likelihood and its gradient with respect to the five logits, all in float64 registers.
+//   * The weight-table gradient  d mat[j, s, :] = sum_k 1[s_j(k) = s] g(k)  is a contraction over the rows k of a one-hot
+//     matrix with the logit gradients, and runs on the tensor cores EXACTLY: a tile's four logit gradients are rounded to
+//     64-bit fixed point (power-of-two scale chosen per tile from the largest |g| in it, four scale classes 2^12 apart) and
+//     split into eight balanced base-256 digits; the warp writes the digits (B operand, 32 rows x 32 int8) and the one-hot
+//     rows (A operand, 128 (position, letter) rows x 32 k-mers, uint8) into its shared-memory slab in the canonical
+//     MN-major layout; warp 15 issues one tcgen05.mma (kind::i8, M 128 x N 32 x K 32) per tile into the tensor-memory
+//     accumulator of the tile's scale class.  Integer sums are order-independent: no atomics, no ranking of equal keys,
+//     bit-reproducible.  Every 2^21 rows per CTA (and at the end) the S32 accumulators are read back (tcgen05.ld),
+//     recombined and added to float64 totals.  The start symbol's gradient is (sum over all rows) - (sum over the four
+//     letters), taken on the integer digit sums.
+// Rounding: |error| <= 2^-45 x (largest |g| of the row's tile) per row, typically 2^-51; see tests/test_gpu_parity.py.
+#include <math.h>
+#include <stdlib.h>
+
+#include "bear_b200.h"
+#include "bear_host.h"
+#include "bear_linear_head.cuh"
+#include "bear_sm100.cuh"
+
+namespace {
+
+using namespace bear;
+using namespace bear::sm100;
+
+constexpr int T3_THREADS = 512;
+constexpr int T3_NW = T3_THREADS / 32;
+constexpr int T3_NPROD = T3_NW - 1;        // warps 0..14 compute rows, warp 15 issues the tensor-core work
+constexpr int SLAB_A = 4096;               // one-hot operand of a tile: 8 groups of 16 (position, letter) rows x 32 k-mers
+constexpr int SLAB_B = 1024;               // digit operand of a tile: 2 groups of 16 digit columns x 32 k-mers
+constexpr int STAGE_BYTES = 256 + A1 * 128;   // k-mer plane + five count planes of a 32-row tile
+constexpr int MAX_STAGES = 4;
+constexpr int NCLS = 4;                    // fixed-point scale classes; scale of class c = 2^(56 - 12 c)
+constexpr int FLUSH_IT = (1 << 21) / (T3_NPROD * 32);   // iterations between accumulator read-backs (|digit sum| < 2^28)
+constexpr uint32_t TMEM_COLS = 128;        // NCLS accumulators of 32 columns
+constexpr uint64_t DIGIT_BIAS = 0x0080808080808080ull;
+
+struct Train3Layout {                      // offsets in bytes from the start of dynamic shared memory
+    int R, slab_a, slab_b, ring, acc, acc_start, ones, tab_lg, tab_dg, stir, symtab, red, bars, misc, total;
+};
+
+__host__ __device__ inline Train3Layout train3_layout(int nch, int nstage) {
+    Train3Layout L;
+    int o = 0;
+    L.R = o;          o += nch * ENT * 4 * 8;
+    o = (o + 127) & ~127;
+    L.slab_a = o;     o += T3_NPROD * SLAB_A;
+    L.slab_b = o;     o += T3_NPROD * SLAB_B;
+    L.ring = o;       o += T3_NPROD * nstage * STAGE_BYTES;
+    L.acc = o;        o += 128 * 4 * 8;          // [(position, letter) row][logit] float64 totals
+    L.acc_start = o;  o += 32 * 4 * 8;           // [position][logit] totals of the start symbol
+    L.ones = o;       o += 32 * 4;               // digit sums of the all-rows operand row (one scale class at a time)
+    L.tab_lg = o;     o += TABN * 8;
+    L.tab_dg = o;     o += TABN * 8;
+    L.stir = o;       o += ((STIR_N * 4 + 15) / 16) * 16;
+    L.symtab = o;     o += 2 * ENT * 2;
+    L.red = o;        o += 32 * 8;
+    L.bars = o;       o += (2 * T3_NPROD + T3_NPROD * MAX_STAGES + 1) * 8;
+    L.misc = o;       o += 64;                   // tmem base, classes in use, non-finite flag, per-slab class bytes
+    L.total = o;
+    return L;
+}
+
+// one-hot words of four consecutive positions: byte `s` of word p is 1 for letter s of position 4 g + p.  `x` holds the
+// 2-bit symbols left-aligned, `sh` = bit offset of the group's 8 bits in x.
+template <int SH>
+__device__ __forceinline__ uint4 onehot_group(uint32_t x) {
+    uint4 w;
+    w.x = 1u << ((x >> (SH + 3)) & 24u);
+    w.y = 1u << ((x >> (SH + 1)) & 24u);
+    w.z = 1u << ((SH >= 1 ? (x >> (SH >= 1 ? SH - 1 : 0)) : (x << 1)) & 24u);
+    w.w = 1u << ((SH >= 3 ? (x >> (SH >= 3 ? SH - 3 : 0)) : (x << 3)) & 24u);
+    return w;
+}
+
+// Reads the S32 digit sums of every scale class in use back from tensor memory (warps 0..3: thread = operand row),
+// recombines them and adds them to the float64 totals.  Called by every thread of the CTA, between CTA barriers.
+__device__ __noinline__ void flush_accumulators(uint32_t tmem, uint32_t used, int lag, double* acc, double* acc_start, int32_t* ones) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int c = 0; c < NCLS; ++c) {
+        if (!((used >> c) & 1u)) continue;           // (uniform over the CTA)
+        uint32_t d[32];
+        const int m = warp * 32 + lane;              // operand row of this thread (warps 0..3)
+        if (warp < 4) {
+            tmem_ld32(tmem + (uint32_t(warp * 32) << 16) + c * 32, d);
+            if (m == 4 * lag) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) ones[i] = int32_t(d[i]);
+            }
+        }
+        __syncthreads();
+        if (warp < 4) {
+            const double inv_scale = __hiloint2double((1023 - 56 + 12 * c) << 20, 0);
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                int64_t lo = 0, hi = 0, slo = 0, shi = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int32_t dl = int32_t(d[8 * b + i]), dh = int32_t(d[8 * b + 4 + i]);
+                    const int64_t wgt = int64_t(1) << (8 * i);
+                    lo += int64_t(dl) * wgt;
+                    hi += int64_t(dh) * wgt;
+                    // start symbol of this position: all rows minus the four letters (the lanes of a quad)
+                    int32_t ql = dl + __shfl_xor_sync(0xffffffffu, dl, 1);
+                    ql += __shfl_xor_sync(0xffffffffu, ql, 2);
+                    int32_t qh = dh + __shfl_xor_sync(0xffffffffu, dh, 1);
+                    qh += __shfl_xor_sync(0xffffffffu, qh, 2);
+                    slo += int64_t(ones[8 * b + i] - ql) * wgt;
+                    shi += int64_t(ones[8 * b + 4 + i] - qh) * wgt;
+                }
+                acc[m * 4 + b] += fma(double(hi), 4294967296.0, double(lo)) * inv_scale;
+                if ((m & 3) == 0 && m < 4 * lag)
+                    acc_start[(m >> 2) * 4 + b] += fma(double(shi), 4294967296.0, double(slo)) * inv_scale;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <bool TRAIN_AR>
+__global__ void __launch_bounds__(T3_THREADS, 1)
+linear_train_tc_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ col, int64_t stride, int64_t row_lo,
+                       int64_t row_hi, int lag, const ChunkKeys ck, int nstage, int use_tma, const double* __restrict__ mat,
+                       const double* __restrict__ h_signed, double* __restrict__ ll_out, double* __restrict__ partials) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int nch = num_chunks(lag);
+    const Train3Layout L = train3_layout(nch, nstage);
+    double* R = reinterpret_cast<double*>(smem_raw + L.R);                // [nch][ENT][4] forward ratios
+    double* acc = reinterpret_cast<double*>(smem_raw + L.acc);
+    double* acc_start = reinterpret_cast<double*>(smem_raw + L.acc_start);
+    int32_t* ones = reinterpret_cast<int32_t*>(smem_raw + L.ones);
+    double* tab_lg = reinterpret_cast<double*>(smem_raw + L.tab_lg);
+    double* tab_dg = reinterpret_cast<double*>(smem_raw + L.tab_dg);
+    float* stir = reinterpret_cast<float*>(smem_raw + L.stir);
+    uint16_t* symtab = reinterpret_cast<uint16_t*>(smem_raw + L.symtab);
+    double* red = reinterpret_cast<double*>(smem_raw + L.red);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + L.bars);
+    volatile uint32_t* misc = reinterpret_cast<volatile uint32_t*>(smem_raw + L.misc);   // [0] tmem base [1] classes [2] non-finite
+    volatile uint8_t* slab_cls = reinterpret_cast<volatile uint8_t*>(smem_raw + L.misc + 16);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool producer = warp < T3_NPROD;
+    const double hinv = exp(-h_signed[0]);                  // 1 / h,  h = exp(h_signed)  (bear_net.py:186)
+    const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * T3_NPROD, bar_in = bar_empty + 8 * T3_NPROD,
+                   bar_done = bar_in + 8 * T3_NPROD * MAX_STAGES;
+
+    // ---------------- tables, barriers, tensor memory ----------------
+    for (int i = threadIdx.x; i < 128 * 4 + 32 * 4; i += blockDim.x) acc[i] = 0.0;     // acc and acc_start are adjacent
+    for (int i = threadIdx.x; i < STIR_N; i += blockDim.x) stir[i] = float(kStirling[i]);
+    for (int i = threadIdx.x; i < T3_NPROD * (SLAB_A + SLAB_B) / 4; i += blockDim.x)
+        reinterpret_cast<uint32_t*>(smem_raw + L.slab_a)[i] = 0u;
+    if (!TRAIN_AR && threadIdx.x < TABN) {
+        // the concentrations of a row sum to 1/h + 5 eps whatever its k-mer (softmax sums to 1)
+        const LgDg t = lgdg_diff<true>(hinv + A1 * BEAR_EPS, double(threadIdx.x));
+        tab_lg[threadIdx.x] = t.add + (t.mul == 1.0 ? 0.0 : log(t.mul));
+        tab_dg[threadIdx.x] = t.dg;
+    }
+    if (threadIdx.x == 0) {
+        for (int w = 0; w < T3_NPROD; ++w) {
+            mbar_init(bar_full + 8 * w, 1);
+            mbar_init(bar_empty + 8 * w, 1);
+            for (int s = 0; s < MAX_STAGES; ++s) mbar_init(bar_in + 8 * (w * MAX_STAGES + s), 1);
+        }
+        mbar_init(bar_done, 1);
+        mbar_fence_init();
+        misc[1] = 0u;
+        misc[2] = 0u;
+    }
+    if (warp == T3_NPROD) tmem_alloc(smem_u32(const_cast<uint32_t*>(&misc[0])), TMEM_COLS);
+    build_ext_tables(mat, R, symtab, lag, ck);
+    fence_proxy_async();                                     // the zeroed slabs are read by the tensor cores
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = misc[0];
+
+    // tiles are aligned to absolute multiples of 32 rows (128-byte aligned planes); rows outside [row_lo, row_hi) are dead
+    const int64_t a0 = row_lo & ~int64_t(31);
+    const int64_t ntiles = (row_hi - a0 + 31) >> 5;
+    const int64_t per_iter = int64_t(gridDim.x) * T3_NPROD;
+    const int64_t niter = (ntiles + per_iter - 1) / per_iter;
+    auto tile_of = [&](int64_t it, int w) { return (it * gridDim.x + blockIdx.x) * T3_NPROD + w; };
+    // a tile is fetched by the TMA engine when all of its 32 rows lie below row_hi (the tail tile uses guarded loads)
+    auto tma_tile = [&](int64_t t) { return use_tma && t < ntiles && a0 + (t << 5) + 32 <= row_hi; };
+
+    double acc_add = 0.0, dh_sum = 0.0;
+    LogProdLong acc_prod;
+    const int ngrp = lag / 4 + 1;                           // 16-row groups of the one-hot operand that carry data
+    unsigned char* ring = smem_raw + L.ring + warp * nstage * STAGE_BYTES;
+    const uint32_t my_in = bar_in + 8 * warp * MAX_STAGES;
+
+    auto issue_tile = [&](int64_t t, int stg) {             // lane 0 only
+        const uint32_t bar = my_in + 8 * stg, dst = smem_u32(ring + stg * STAGE_BYTES);
+        const int64_t r0 = a0 + (t << 5);
+        mbar_arrive_expect_tx(bar, STAGE_BYTES);
+        bulk_g2s(dst, kmers + r0, 256, bar);
+#pragma unroll
+        for (int b = 0; b < A1; ++b) bulk_g2s(dst + 256 + b * 128, col + b * stride + r0, 128, bar);
+    };
+
+    if (producer && lane == 0) {
+        for (int s = 0; s < nstage; ++s) {
+            const int64_t t = tile_of(s, warp);
+            if (s < niter && tma_tile(t)) issue_tile(t, s);
+        }
+    }
+
+    int stg = 0;
+    uint32_t in_par = 0, flushes = 0;
+    uint32_t cls_used = 0;                                  // issuer: accumulators holding data since the last read-back
+    for (int64_t it = 0; it < niter; ++it) {
+        if (producer) {
+            const int64_t t = tile_of(it, warp);
+            if (t < ntiles) {
+                const int64_t arow = a0 + (t << 5) + lane;
+                const bool in_range = arow >= row_lo && arow < row_hi;
+                uint64_t code;
+                Counts r;
+                if (tma_tile(t)) {
+                    mbar_wait(my_in + 8 * stg, in_par);
+                    const unsigned char* st = ring + stg * STAGE_BYTES;
+                    code = reinterpret_cast<const uint64_t*>(st)[lane];
+#pragma unroll
+                    for (int b = 0; b < A1; ++b) r.c[b] = reinterpret_cast<const uint32_t*>(st + 256)[b * 32 + lane];
+                } else {
+                    code = in_range ? __ldg(kmers + arow) : 0ull;
+#pragma unroll
+                    for (int b = 0; b < A1; ++b) r.c[b] = in_range ? __ldg(col + b * stride + arow) : 0u;
+                }
+                if (!in_range) {
+                    code = 0ull;
+#pragma unroll
+                    for (int b = 0; b < A1; ++b) r.c[b] = 0u;
+                }
+                r.cmax = max(max(max(r.c[0], r.c[1]), max(r.c[2], r.c[3])), r.c[4]);
+                if (r.cmax < (1u << 29))
+                    r.n = double((r.c[0] + r.c[1]) + (r.c[2] + r.c[3]) + r.c[4]);
+                else
+                    r.n = (double(r.c[0]) + double(r.c[1])) + (double(r.c[2]) + double(r.c[3])) + double(r.c[4]);
+                const bool live = r.cmax != 0;              // zero-count row: ll = 0 and every gradient is 0
+                const uint32_t steps = warp_steps(live, r.cmax);   // (a warp collective: every lane has read its stage)
+                __syncwarp();
+                if (lane == 0) {                            // refill this stage with the tile of iteration it + nstage
+                    const int64_t t2 = tile_of(it + nstage, warp);
+                    if (it + nstage < niter && tma_tile(t2)) issue_tile(t2, stg);
+                }
+                const int ns = int(code >> 58);
+                const uint64_t v = code & PAYLOAD_MASK;
+                // ---- head: product of chunk-table rows ----
+                double f[A1];
+                {
+                    double p0 = 1.0, p1 = 1.0, p2 = 1.0, p3 = 1.0;
+                    int sh = 2 * lag, c0 = 0;
+                    for (int ch = 0; ch < nch; ++ch) {
+                        const int rr = ck.base + (ch < ck.extra ? 1 : 0);
+                        sh -= 2 * rr;
+                        int q = int(uint32_t(v >> sh) & ((1u << (2 * rr)) - 1u));
+                        if (ns > c0) q = ext_key(uint32_t(q), rr, ns - c0);
+                        c0 += rr;
+                        const int sw = half_swizzle(q);
+                        const double2 a = *reinterpret_cast<const double2*>(R + (ch * ENT + q) * 4 + sw);
+                        const double2 b = *reinterpret_cast<const double2*>(R + (ch * ENT + q) * 4 + (sw ^ 2));
+                        p0 *= a.x;
+                        p1 *= a.y;
+                        p2 *= b.x;
+                        p3 *= b.y;
+                    }
+                    const double z = 1.0 + ((p0 + p1) + (p2 + p3));
+                    if (z < 1e300 && z > 1e-300) {
+                        const double zi = 1.0 / z;
+                        f[0] = p0 * zi;
+                        f[1] = p1 * zi;
+                        f[2] = p2 * zi;
+                        f[3] = p3 * zi;
+                        f[4] = zi;
+                    } else {
+                        linear_head_exact(mat, code, lag, f);
+                    }
+                }
+                // ---- likelihood and its gradient with respect to the logits ----
+                double g[4], ll_row = 0.0;
+                {
+                    double add, prod, w[A1];
+                    if (TRAIN_AR) {
+                        double p[A1], ri[A1];
+#pragma unroll
+                        for (int b = 0; b < A1; ++b) p[b] = f[b] + BEAR_EPS;                 // bear_net.py:68
+                        mn_term(p, r, add, prod);
+                        inv5(p, ri);
+                        double u = 0.0;
+#pragma unroll
+                        for (int b = 0; b < A1; ++b) {
+                            w[b] = double(r.c[b]) * ri[b];                                   // d ll / d f_b
+                            u = fma(f[b], w[b], u);
+                        }
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) g[b] = f[b] * (w[b] - u);
+                    } else {
+                        double conc[A1];
+#pragma unroll
+                        for (int b = 0; b < A1; ++b) conc[b] = fma(f[b], hinv, BEAR_EPS);       // bear_net.py:43
+                        letters_term<true>(stir, conc, r, steps, add, prod, w);
+                        double tadd, tdg;
+                        if (r.n < double(TABN)) {
+                            tadd = tab_lg[int(r.n)];
+                            tdg = tab_dg[int(r.n)];
+                        } else {
+                            double tprod;
+                            const double s = ((conc[0] + conc[1]) + (conc[2] + conc[3])) + conc[4];
+                            total_term<true>(s, r, tadd, tprod, tdg);
+                            tadd += log(tprod);
+                        }
+                        add -= tadd;
+                        // d ll/d conc_b = w_b - tdg; d ll/d f_b = that / h; softmax backward:
+                        // g_b = f_b (d ll/d f_b - sum_j f_j d ll/d f_j) = f_b (w_b - W) / h,  W = sum_j f_j w_j
+                        double W = 0.0;
+#pragma unroll
+                        for (int b = 0; b < A1; ++b) W = fma(f[b], w[b], W);
+                        if (live) dh_sum -= (W - tdg) * hinv;   // d ll / d h_signed = -sum_b f_b d ll/d f_b
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) g[b] = f[b] * hinv * (w[b] - W);
+                    }
+                    if (live) {
+                        if (ll_out) {
+                            ll_row = add + log(prod);
+                            acc_add += ll_row;
+                        } else {
+                            acc_add += add;
+                            acc_prod.push(0.0, prod);
+                        }
+                    }
+                }
+                if (ll_out && in_range) ll_out[arow - row_lo] = ll_row;
+                // ---- fixed-point digits of the logit gradients: scale class from the largest |g| of the tile ----
+                uint32_t hmax = 0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    if (!live) g[b] = 0.0;
+                    hmax = max(hmax, uint32_t(__double2hiint(g[b])) & 0x7fffffffu);
+                }
+                hmax = __reduce_max_sync(0xffffffffu, hmax);
+                const int ex = int(hmax >> 20) - 1023;       // floor(log2 max|g|);  |g| <= row total < 2^35 by construction
+                const int cls = ex < 6 ? 0 : ex < 18 ? 1 : ex < 30 ? 2 : 3;
+                if (ex >= 42 && lane == 0) misc[2] = 1u;     // inf / nan (diverged parameters): the gradient is reported as nan
+                const double scale = __hiloint2double((1023 + 56 - 12 * cls) << 20, 0);
+                uint64_t z[4];
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    z[b] = (uint64_t(__double2ll_rn(g[b] * scale)) + DIGIT_BIAS) ^ DIGIT_BIAS;   // balanced base-256 digits
+                // ---- operands of the tile's tensor-core product ----
+                if (it > 0) mbar_wait(bar_empty + 8 * warp, uint32_t(it - 1) & 1u);   // the previous product has read the slab
+                {
+                    unsigned char* sb = smem_raw + L.slab_b + warp * SLAB_B + lane * 16;
+                    *reinterpret_cast<uint4*>(sb) = make_uint4(uint32_t(z[0]), uint32_t(z[0] >> 32), uint32_t(z[1]), uint32_t(z[1] >> 32));
+                    *reinterpret_cast<uint4*>(sb + 512) = make_uint4(uint32_t(z[2]), uint32_t(z[2] >> 32), uint32_t(z[3]), uint32_t(z[3] >> 32));
+                    // one-hot rows m = 4 j + s (letters s of position j); the zero padding below the last position makes
+                    // row 4 lag the all-rows row
+                    const uint64_t vl = v << (64 - 2 * lag);
+                    const uint32_t xh = uint32_t(vl >> 32), xl = uint32_t(vl);
+                    const bool any_start = __any_sync(0xffffffffu, ns > 0);
+                    unsigned char* sa = smem_raw + L.slab_a + warp * SLAB_A + lane * 16;
+                    auto put_group = [&](int gI, uint4 w) {
+                        if (gI >= ngrp) return;
+                        if (any_start) {                     // positions under the start run select no letter
+                            if (ns > 4 * gI) w.x = 0u;
+                            if (ns > 4 * gI + 1) w.y = 0u;
+                            if (ns > 4 * gI + 2) w.z = 0u;
+                            if (ns > 4 * gI + 3) w.w = 0u;
+                        }
+                        *reinterpret_cast<uint4*>(sa + gI * 512) = w;
+                    };
+                    put_group(0, onehot_group<24>(xh));
+                    put_group(1, onehot_group<16>(xh));
+                    put_group(2, onehot_group<8>(xh));
+                    put_group(3, onehot_group<0>(xh));
+                    put_group(4, onehot_group<24>(xl));
+                    put_group(5, onehot_group<16>(xl));
+                    put_group(6, onehot_group<8>(xl));
+                    put_group(7, onehot_group<0>(xl));
+                    if (lane == 0) slab_cls[warp] = uint8_t(cls);
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_full + 8 * warp);
+            }
+            if (++stg == nstage) {
+                stg = 0;
+                in_par ^= 1u;
+            }
+        } else if (lane == 0) {
+            // ---------------- tensor-core issuer: one product per staged tile, in warp order ----------------
+            const uint32_t idesc = umma_idesc_i8(128, 32);
+            for (int w = 0; w < T3_NPROD; ++w) {
+                if (tile_of(it, w) >= ntiles) break;
+                mbar_wait(bar_full + 8 * w, uint32_t(it) & 1u);
+                tc_fence_after();
+                const uint32_t cls = slab_cls[w];
+                const uint64_t da = umma_desc(smem_u32(smem_raw + L.slab_a + w * SLAB_A), 128, 512);
+                const uint64_t db = umma_desc(smem_u32(smem_raw + L.slab_b + w * SLAB_B), 128, 512);
+                umma_i8(tmem + cls * 32, da, db, idesc, (cls_used >> cls) & 1u);
+                cls_used |= 1u << cls;
+                umma_commit(bar_empty + 8 * w);
+            }
+        }
+        // ---------------- read the accumulators back before a digit sum can leave 32 bits, and at the end ----------------
+        if ((it + 1) % FLUSH_IT == 0 || it + 1 == niter) {
+            if (!producer && lane == 0) {
+                umma_commit(bar_done);
+                mbar_wait(bar_done, flushes & 1u);
+                misc[1] = cls_used;
+                cls_used = 0;
+            }
+            ++flushes;
+            tc_fence_before();
+            __syncthreads();
+            tc_fence_after();
+            flush_accumulators(tmem, misc[1], lag, acc, acc_start, ones);
+            tc_fence_before();
+            __syncthreads();
+        }
+    }
+
+    if (warp == T3_NPROD) tmem_dealloc(tmem, TMEM_COLS);
+    const int P = 2 + lag * A1 * A1;
+    double* out = partials + int64_t(blockIdx.x) * P;
+    const double ll_thread = acc_add + acc_prod.value();
+    const double ll_blk = block_sum(ll_thread, red);
+    const double dh_blk = block_sum(dh_sum, red);
+    if (threadIdx.x == 0) {
+        out[0] = ll_blk;
+        out[1] = dh_blk;
+    }
+    __syncthreads();
+    // d ll / d mat[j, s, b]: letters from the operand rows, the start symbol (s = 4) from its own totals; the five logit
+    // gradients of a row sum to zero, which gives b = 4
+    const bool bad = misc[2] != 0u;
+    for (int idx = threadIdx.x; idx < lag * A1 * A1; idx += blockDim.x) {
+        const int b = idx % A1, s = (idx / A1) % A1, j = idx / (A1 * A1);
+        const double* src = s < 4 ? acc + (4 * j + s) * 4 : acc_start + j * 4;
+        const double val = b < 4 ? src[b] : -((src[0] + src[1]) + (src[2] + src[3]));
+        out[2 + idx] = bad ? nan("") : val;
+    }
+}
+
+}  // namespace
+
+extern "C" int64_t bear_workspace_doubles(int64_t n, int lag, int nparams) {
+    (void)n;
+    int64_t p = 2 + int64_t(lag) * A1 * A1;
+    if (nparams + 2 > p) p = nparams + 2;
+    if (p < 64) p = 64;
+    return int64_t(MAX_GRID) * p;
+}
+
+extern "C" int bear_linear_train_step(const uint64_t* d_kmers, const uint32_t* d_col, int64_t stride,
+                                      int64_t row0, int64_t n, int lag, const double* d_mat,
+                                      const double* d_h_signed, double scale, int train_ar,
+                                      double* d_flat, double* d_ll_out, double* d_workspace, void* stream) {
+    const char* fn = "bear_linear_train_step";
+    BEAR_REQUIRE(d_kmers && d_col && d_mat && d_h_signed && d_flat && d_workspace, fn);
+    BEAR_REQUIRE(n >= 0 && row0 >= 0 && stride >= row0 + n, fn);
+    BEAR_REQUIRE(lag >= 1 && lag <= 29, fn);
+    if (n == 0) return BEAR_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int P = 2 + lag * A1 * A1;
+    const ChunkKeys ck = make_chunk_keys(lag);
+    const int nch = num_chunks(lag);
+    int nstage = MAX_STAGES;
+    while (nstage > 2 && size_t(train3_layout(nch, nstage).total) > size_t(227 * 1024)) --nstage;
+    const size_t smem = size_t(train3_layout(nch, nstage).total);
+    // bulk copies need 16-byte aligned planes: tiles start at absolute multiples of 32 rows, so this is a property of
+    // the table (base pointers, plane pitch), not of the batch
+    const int use_tma = (reinterpret_cast<uintptr_t>(d_kmers) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_col) & 15) == 0 &&
+                        (stride & 3) == 0;
+    const int64_t a0 = row0 & ~int64_t(31);
+    const int64_t ntiles = (row0 + n - a0 + 31) / 32;
+    const int64_t want = (ntiles + T3_NPROD - 1) / T3_NPROD;
+    const int grid = int(want < 148 ? want : 148);
+    if (train_ar) {
+        BEAR_CUDA_CHECK(cudaFuncSetAttribute(linear_train_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        linear_train_tc_kernel<true><<<grid, T3_THREADS, smem, st>>>(d_kmers, d_col, stride, row0, row0 + n, lag, ck, nstage, use_tma,
+                                                                    d_mat, d_h_signed, d_ll_out, d_workspace);
+    } else {
+        BEAR_CUDA_CHECK(cudaFuncSetAttribute(linear_train_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        linear_train_tc_kernel<false><<<grid, T3_THREADS, smem, st>>>(d_kmers, d_col, stride, row0, row0 + n, lag, ck, nstage, use_tma,
+                                                                     d_mat, d_h_signed, d_ll_out, d_workspace);
+    }
+    BEAR_LAUNCH_CHECK("linear_train_tc_kernel");
+    reduce_partials_kernel<<<(P + 127) / 128, 128, 0, st>>>(d_workspace, grid, P, -scale, d_flat);
+    BEAR_LAUNCH_CHECK("reduce_partials_kernel");
+    return BEAR_OK;
+}

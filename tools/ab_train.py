@@ -1,4 +1,7 @@
-"""Quick A/B timing of the fused linear train / eval kernels (CUDA events) for kernel experiments."""
+"""A/B timing of the fused linear train / eval kernels on synthetic tables (CUDA events, inputs >> L2).
+If the library also exports bear_linear_train_step_legacy (a previous kernel kept for comparison) it is timed too and
+its outputs are compared."""
+import ctypes
 import os
 import sys
 
@@ -13,8 +16,15 @@ dev = torch.device('cuda', 0)
 torch.cuda.set_device(dev)
 n = int(os.environ.get('ROWS', 1 << 27))
 tag = os.environ.get('TAG', '')
+cases = os.environ.get('CASES', 'lag20,lag20-sorted,lag13,lag20-dense').split(',')
+legacy = getattr(ctypes.CDLL(_lib.LIB_PATH), 'bear_linear_train_step_legacy', None)
+if legacy is not None:
+    legacy.restype = ctypes.c_int
+    legacy.argtypes = lib.bear_linear_train_step.argtypes
 out = []
 for lag, regime, name in ((20, 0, 'lag20'), (20, 2, 'lag20-sorted'), (13, 0, 'lag13'), (20, 1, 'lag20-dense')):
+    if name not in cases:
+        continue
     stride = (n + 3) // 4 * 4
     kmers = torch.empty(stride, dtype=torch.int64, device=dev)
     counts = torch.empty((1, 5, stride), dtype=torch.int32, device=dev)
@@ -27,27 +37,28 @@ for lag, regime, name in ((20, 0, 'lag20'), (20, 2, 'lag20-sorted'), (13, 0, 'la
     alpha = torch.tensor([0.1, 1.0, 10.0], dtype=torch.float64, device=dev)
     eacc = torch.zeros(11, dtype=torch.float64, device=dev)
 
-    def train():
-        check(lib.bear_linear_train_step(ptr(kmers), ptr(counts), stride, 0, n, lag, ptr(mat), ptr(hs), 1.0, 0, ptr(flat), None,
-                                         ptr(ws), _lib.stream()))
+    def train(fn=lib.bear_linear_train_step):
+        check(fn(ptr(kmers), ptr(counts), stride, 0, n, lag, ptr(mat), ptr(hs), 1.0, 0, ptr(flat), None, ptr(ws), _lib.stream()))
 
     def evalk():
         check(lib.bear_eval_step(ptr(kmers), ptr(counts), None, stride, 0, n, lag, _lib.HEAD_LINEAR, ptr(mat), ptr(h), 1,
                                  ptr(alpha), 3, 7, ptr(eacc), ptr(ws), _lib.stream()))
-    for fn, kn in ((train, 'train'), (evalk, 'eval')):
+    fns = [(train, 'train'), (evalk, 'eval')]
+    if legacy is not None:
+        flat.zero_()
+        train()
+        new = flat.clone()
+        flat.zero_()
+        train(legacy)
+        old = flat.clone()
+        err = float((new[2:] - old[2:]).abs().max() / old[2:].abs().max())
+        out.append('%s: new vs legacy gradient %.2e (rel. to largest), loss %.2e, dh %.2e' % (
+            name, err, abs(float(new[0] - old[0]) / float(old[0])), abs(float(new[1] - old[1]) / float(old[1]))))
+        fns.insert(1, (lambda: train(legacy), 'train-legacy'))
+    for fn, kn in fns:
         for _ in range(2):
             fn()
         torch.cuda.synchronize()
-        cyc = None
-        if kn == 'train' and hasattr(lib, 'bear_debug_train_cycles'):      # built with -DBEAR_TRAIN_EXPERIMENTS
-            import ctypes
-            cyc = (ctypes.c_ulonglong * 5)()
-            lib.bear_debug_train_cycles(cyc)                                # clear
-            fn()
-            lib.bear_debug_train_cycles(cyc)
-            ctas = max(1, (cyc[3] + cyc[4]) // 16)
-            out.append('%s busy: producers %.2f, consumers %.2f of the kernel loop' % (
-                name, cyc[0] / max(1, cyc[2] * cyc[3] / ctas), cyc[1] / max(1, cyc[2] * cyc[4] / ctas)))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(5):
@@ -57,4 +68,4 @@ for lag, regime, name in ((20, 0, 'lag20'), (20, 2, 'lag20-sorted'), (13, 0, 'la
         ms = e0.elapsed_time(e1) / 5
         out.append('%s %s: %.3f ms (%.3e rows/s)' % (name, kn, ms, n / ms * 1e3))
     del kmers, counts
-print(tag, ' | '.join(out))
+print(tag, '\n'.join(out))
