@@ -27,7 +27,17 @@ def _load():
         raise ImportError(
             'libbear_b200.so is missing (%s). Build it with `python -m bear_b200.build`; '
             'bear_b200 has no CPU or pure-PyTorch fallback.' % LIB_PATH)
-    return ctypes.CDLL(LIB_PATH)
+    handle = ctypes.CDLL(LIB_PATH)
+    if not os.environ.get('BEAR_B200_LIB'):
+        # a binary older than the sources next to it (e.g. after a pull) is refused, never loaded silently;
+        # on a box without the sources' compiler the prebuilt library must match the sources it shipped with
+        from . import build as _build
+        want = _build._digest()
+        have = _build.library_digest(LIB_PATH)
+        if have != want:
+            raise ImportError('libbear_b200.so is stale: built from sources %s, tree is %s. Rebuild with '
+                              '`python -m bear_b200.build`.' % (str(have)[:12], want[:12]))
+    return handle
 
 
 lib = _load()
@@ -38,6 +48,7 @@ _pi64, _pi32 = ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int)
 _SIGNATURES = {
     'bear_last_error': (_cp, []),
     'bear_version': (_i32, []),
+    'bear_build_digest': (_cp, []),
     'bear_alphabet_size': (_i32, [_i32]),
     'bear_max_lag': (_i32, [_i32]),
     'bear_count_rows': (_i64, [_cp, _i32]),

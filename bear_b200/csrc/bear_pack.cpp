@@ -32,6 +32,11 @@ void bear_set_error(const char* fmt, ...) {
 
 extern "C" const char* bear_last_error(void) { return g_err; }
 extern "C" int bear_version(void) { return 1; }
+#ifndef BEAR_BUILD_DIGEST
+#define BEAR_BUILD_DIGEST "unknown"
+#endif
+static const char g_build_digest[] = "BEAR_BUILD_DIGEST:" BEAR_BUILD_DIGEST;
+extern "C" const char* bear_build_digest(void) { return g_build_digest + 18; }
 
 extern "C" int bear_alphabet_size(int alphabet) {
     if (alphabet == BEAR_ALPHABET_DNA || alphabet == BEAR_ALPHABET_RNA) return 4;

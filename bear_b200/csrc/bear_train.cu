@@ -12,8 +12,10 @@
 //     64-bit fixed point (power-of-two scale chosen per tile from the largest |g| in it, four scale classes 2^12 apart) and
 //     split into eight balanced base-256 digits; the warp writes the digits (B operand, 32 rows x 32 int8) and the one-hot
 //     rows (A operand, 128 (position, letter) rows x 32 k-mers, uint8) into its shared-memory slab in the canonical
-//     MN-major layout; warp 15 issues one tcgen05.mma (kind::i8, M 128 x N 32 x K 32) per tile into the tensor-memory
-//     accumulator of the tile's scale class.  Integer sums are order-independent: no atomics, no ranking of equal keys,
+//     MN-major layout and publishes a sequence byte; one thread of warp 15 polls the 15 bytes with a single 128-bit
+//     load and issues one tcgen05.mma (kind::i8, M 128 x N 32 x K 32) per staged tile into the tensor-memory
+//     accumulator of the tile's scale class (issuing a tcgen05.mma stalls the issuing warp for > 100 cycles, so the
+//     row pipelines do not issue their own).  Integer sums are order-independent: no atomics, no ranking of equal keys,
 //     bit-reproducible.  Every 2^21 rows per CTA (and at the end) the S32 accumulators are read back (tcgen05.ld),
 //     recombined and added to float64 totals.  The start symbol's gradient is (sum over all rows) - (sum over the four
 //     letters), taken on the integer digit sums.
@@ -31,7 +33,10 @@ namespace {
 using namespace bear;
 using namespace bear::sm100;
 
-constexpr int T3_THREADS = 512;
+#ifndef BEAR_T3_THREADS
+#define BEAR_T3_THREADS 512
+#endif
+constexpr int T3_THREADS = BEAR_T3_THREADS;
 constexpr int T3_NW = T3_THREADS / 32;
 constexpr int T3_NPROD = T3_NW - 1;        // warps 0..14 compute rows, warp 15 issues the tensor-core work
 constexpr int SLAB_A = 4096;               // one-hot operand of a tile: 8 groups of 16 (position, letter) rows x 32 k-mers
@@ -47,14 +52,13 @@ struct Train3Layout {                      // offsets in bytes from the start of
     int R, slab_a, slab_b, ring, acc, acc_start, ones, tab_lg, tab_dg, stir, symtab, red, bars, misc, total;
 };
 
-__host__ __device__ inline Train3Layout train3_layout(int nch, int nstage) {
-    Train3Layout L;
+__host__ __device__ constexpr Train3Layout train3_layout(int nch, int nstage) {
+    Train3Layout L{};
     int o = 0;
     L.R = o;          o += nch * ENT * 4 * 8;
     o = (o + 127) & ~127;
     L.slab_a = o;     o += T3_NPROD * SLAB_A;
     L.slab_b = o;     o += T3_NPROD * SLAB_B;
-    L.ring = o;       o += T3_NPROD * nstage * STAGE_BYTES;
     L.acc = o;        o += 128 * 4 * 8;          // [(position, letter) row][logit] float64 totals
     L.acc_start = o;  o += 32 * 4 * 8;           // [position][logit] totals of the start symbol
     L.ones = o;       o += 32 * 4;               // digit sums of the all-rows operand row (one scale class at a time)
@@ -63,8 +67,10 @@ __host__ __device__ inline Train3Layout train3_layout(int nch, int nstage) {
     L.stir = o;       o += ((STIR_N * 4 + 15) / 16) * 16;
     L.symtab = o;     o += 2 * ENT * 2;
     L.red = o;        o += 32 * 8;
-    L.bars = o;       o += (2 * T3_NPROD + T3_NPROD * MAX_STAGES + 1) * 8;
-    L.misc = o;       o += 64;                   // tmem base, classes in use, non-finite flag, per-slab class bytes
+    L.bars = o;       o += (T3_NPROD + T3_NPROD * MAX_STAGES + 1) * 8;
+    L.misc = o;       o += 32;                   // [0] tmem base [1] classes in use [2] non-finite flag; +16: slab status bytes
+    o = (o + 127) & ~127;
+    L.ring = o;       o += T3_NPROD * nstage * STAGE_BYTES;      // last: every other offset is independent of nstage
     L.total = o;
     return L;
 }
@@ -125,15 +131,44 @@ __device__ __noinline__ void flush_accumulators(uint32_t tmem, uint32_t used, in
     }
 }
 
-template <bool TRAIN_AR>
+// chunk geometry of the head tables, precomputed on the host: chunk ch covers positions [c0, c0 + rr) and its key sits
+// `sh` bits above the low end of the packed k-mer
+// running product of many rows' likelihood factors; its binary exponent moves to an integer before it can overflow
+struct LogProdOnly {
+    double mul = 1.0;
+    int ex = 0;
+    __device__ __forceinline__ void push(double, double m) {
+        if (mul > 1e40 || mul < 1e-40) {
+            if (mul > 1e-300 && mul < 1e300) {
+                const int hi = __double2hiint(mul);
+                ex += ((hi >> 20) & 0x7ff) - 1023;
+                mul = __hiloint2double((hi & 0x800fffff) | 0x3ff00000, __double2loint(mul));
+            } else if (mul > 0.0 && mul < 1e-300) {   // towards the subnormal range: rescale by an exact power of two
+                mul *= 0x1p600;
+                ex -= 600;
+            } else if (mul >= 1e300 && mul < INFINITY) {
+                mul *= 0x1p-600;
+                ex += 600;
+            }                              // zero / inf / nan stay: log() gives the reference's -inf / inf / nan
+        }
+        mul *= m;
+    }
+    __device__ __forceinline__ double value() const { return double(ex) * 0.69314718055994530942 + (mul == 1.0 ? 0.0 : log(mul)); }
+};
+
+struct HeadGeom {
+    uint8_t sh[8], rr[8], c0[8];
+};
+
+template <bool TRAIN_AR, int NCH>
 __global__ void __launch_bounds__(T3_THREADS, 1)
 linear_train_tc_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ col, int64_t stride, int64_t row_lo,
-                       int64_t row_hi, int lag, const ChunkKeys ck, int nstage, int use_tma, const double* __restrict__ mat,
-                       const double* __restrict__ h_signed, double* __restrict__ ll_out, double* __restrict__ partials) {
+                       int64_t row_hi, int lag, const ChunkKeys ck, const HeadGeom hg, int nstage, int use_tma,
+                       const double* __restrict__ mat, const double* __restrict__ h_signed, double* __restrict__ ll_out,
+                       double* __restrict__ partials) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int nch = num_chunks(lag);
-    const Train3Layout L = train3_layout(nch, nstage);
-    double* R = reinterpret_cast<double*>(smem_raw + L.R);                // [nch][ENT][4] forward ratios
+    constexpr Train3Layout L = train3_layout(NCH, 0);       // (the ring comes last: no offset depends on nstage)
+    double* R = reinterpret_cast<double*>(smem_raw + L.R);                // [NCH][ENT][4] forward ratios
     double* acc = reinterpret_cast<double*>(smem_raw + L.acc);
     double* acc_start = reinterpret_cast<double*>(smem_raw + L.acc_start);
     int32_t* ones = reinterpret_cast<int32_t*>(smem_raw + L.ones);
@@ -143,14 +178,15 @@ linear_train_tc_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __res
     uint16_t* symtab = reinterpret_cast<uint16_t*>(smem_raw + L.symtab);
     double* red = reinterpret_cast<double*>(smem_raw + L.red);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + L.bars);
-    volatile uint32_t* misc = reinterpret_cast<volatile uint32_t*>(smem_raw + L.misc);   // [0] tmem base [1] classes [2] non-finite
-    volatile uint8_t* slab_cls = reinterpret_cast<volatile uint8_t*>(smem_raw + L.misc + 16);
+    volatile uint32_t* misc = reinterpret_cast<volatile uint32_t*>(smem_raw + L.misc);
+    // status byte of warp w's slab: (tiles staged so far) << 2 | scale class of the staged tile
+    volatile uint8_t* slab_status = reinterpret_cast<volatile uint8_t*>(smem_raw + L.misc + 16);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const bool producer = warp < T3_NPROD;
-    const double hinv = exp(-h_signed[0]);                  // 1 / h,  h = exp(h_signed)  (bear_net.py:186)
-    const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * T3_NPROD, bar_in = bar_empty + 8 * T3_NPROD,
-                   bar_done = bar_in + 8 * T3_NPROD * MAX_STAGES;
+    const double hval = exp(h_signed[0]), hinv = exp(-h_signed[0]);   // h = exp(h_signed)  (bear_net.py:186) and 1 / h
+    // bar_empty[w]: the product of warp w's previous tile has read its slab; bar_in[w][stage]: the stage's bytes have landed;
+    // bar_done: every product issued so far has completed
+    const uint32_t bar_empty = smem_u32(bars), bar_in = bar_empty + 8 * T3_NPROD, bar_done = bar_in + 8 * T3_NPROD * MAX_STAGES;
 
     // ---------------- tables, barriers, tensor memory ----------------
     for (int i = threadIdx.x; i < 128 * 4 + 32 * 4; i += blockDim.x) acc[i] = 0.0;     // acc and acc_start are adjacent
@@ -165,7 +201,6 @@ linear_train_tc_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __res
     }
     if (threadIdx.x == 0) {
         for (int w = 0; w < T3_NPROD; ++w) {
-            mbar_init(bar_full + 8 * w, 1);
             mbar_init(bar_empty + 8 * w, 1);
             for (int s = 0; s < MAX_STAGES; ++s) mbar_init(bar_in + 8 * (w * MAX_STAGES + s), 1);
         }
@@ -173,6 +208,7 @@ linear_train_tc_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __res
         mbar_fence_init();
         misc[1] = 0u;
         misc[2] = 0u;
+        for (int i = 4; i < 8; ++i) misc[i] = 0u;            // slab status bytes
     }
     if (warp == T3_NPROD) tmem_alloc(smem_u32(const_cast<uint32_t*>(&misc[0])), TMEM_COLS);
     build_ext_tables(mat, R, symtab, lag, ck);
@@ -181,64 +217,70 @@ linear_train_tc_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __res
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = misc[0];
-
-    // tiles are aligned to absolute multiples of 32 rows (128-byte aligned planes); rows outside [row_lo, row_hi) are dead
+    // Tiles are aligned to absolute multiples of 32 rows (128-byte aligned planes); rows outside [row_lo, row_hi) are dead.
+    // Iteration i of warp w of CTA c works on tile (i gridDim + c) 15 + w: consecutive warps stream consecutive tiles.
     const int64_t a0 = row_lo & ~int64_t(31);
-    const int64_t ntiles = (row_hi - a0 + 31) >> 5;
-    const int64_t per_iter = int64_t(gridDim.x) * T3_NPROD;
-    const int64_t niter = (ntiles + per_iter - 1) / per_iter;
-    auto tile_of = [&](int64_t it, int w) { return (it * gridDim.x + blockIdx.x) * T3_NPROD + w; };
-    // a tile is fetched by the TMA engine when all of its 32 rows lie below row_hi (the tail tile uses guarded loads)
-    auto tma_tile = [&](int64_t t) { return use_tma && t < ntiles && a0 + (t << 5) + 32 <= row_hi; };
+    const uint32_t ntiles = uint32_t((row_hi - a0 + 31) >> 5);
+    const uint32_t tstep = gridDim.x * T3_NPROD;
+    const uint32_t niter = (ntiles + tstep - 1) / tstep;
+    // tiles below t_full lie entirely below row_hi and are fetched by the TMA engine; the tail tile uses guarded loads
+    const uint32_t t_full = use_tma ? uint32_t((row_hi - a0) >> 5) : 0u;
+    // number of warps holding a tile in the last iteration
+    const int64_t rest = int64_t(ntiles) - (int64_t(niter - 1) * gridDim.x + blockIdx.x) * T3_NPROD;
+    const int nlast = rest < 0 ? 0 : rest > T3_NPROD ? T3_NPROD : int(rest);
 
     double acc_add = 0.0, dh_sum = 0.0;
-    LogProdLong acc_prod;
-    const int ngrp = lag / 4 + 1;                           // 16-row groups of the one-hot operand that carry data
-    unsigned char* ring = smem_raw + L.ring + warp * nstage * STAGE_BYTES;
-    const uint32_t my_in = bar_in + 8 * warp * MAX_STAGES;
+    LogProdOnly acc_prod;
+    uint32_t flushes = 0;
 
-    auto issue_tile = [&](int64_t t, int stg) {             // lane 0 only
-        const uint32_t bar = my_in + 8 * stg, dst = smem_u32(ring + stg * STAGE_BYTES);
-        const int64_t r0 = a0 + (t << 5);
-        mbar_arrive_expect_tx(bar, STAGE_BYTES);
-        bulk_g2s(dst, kmers + r0, 256, bar);
-#pragma unroll
-        for (int b = 0; b < A1; ++b) bulk_g2s(dst + 256 + b * 128, col + b * stride + r0, 128, bar);
-    };
-
-    if (producer && lane == 0) {
-        for (int s = 0; s < nstage; ++s) {
-            const int64_t t = tile_of(s, warp);
-            if (s < niter && tma_tile(t)) issue_tile(t, s);
+    if (warp < T3_NPROD) {
+        const int ngrp = lag / 4 + 1;                       // 16-row groups of the one-hot operand that carry data
+        const uint32_t ring = smem_u32(smem_raw + L.ring) + warp * nstage * STAGE_BYTES;
+        const uint32_t my_in = bar_in + 8 * warp * MAX_STAGES;
+        const uint32_t n_my = niter - (warp < nlast ? 0u : 1u);      // tiles of this warp
+        uint32_t t = blockIdx.x * T3_NPROD + warp;
+        // lanes 0..5 each copy one plane of tile ti: lane 0 the k-mers (256 bytes), lanes 1..5 a count plane (128 bytes)
+        auto issue_tile = [&](uint32_t ti, int stg) {
+            const uint32_t bar = my_in + 8 * stg;
+            const int64_t r0 = a0 + (int64_t(ti) << 5);
+            if (lane == 0) {
+                mbar_arrive_expect_tx(bar, STAGE_BYTES);
+                bulk_g2s(ring + stg * STAGE_BYTES, kmers + r0, 256, bar);
+            } else {
+                bulk_g2s(ring + stg * STAGE_BYTES + 128 + 128 * lane, col + int64_t(lane - 1) * stride + r0, 128, bar);
+            }
+        };
+        if (lane < 6) {
+            for (int s = 0; s < nstage; ++s)
+                if (uint32_t(s) < n_my && t + s * tstep < t_full) issue_tile(t + s * tstep, s);
         }
-    }
-
-    int stg = 0;
-    uint32_t in_par = 0, flushes = 0;
-    uint32_t cls_used = 0;                                  // issuer: accumulators holding data since the last read-back
-    for (int64_t it = 0; it < niter; ++it) {
-        if (producer) {
-            const int64_t t = tile_of(it, warp);
-            if (t < ntiles) {
-                const int64_t arow = a0 + (t << 5) + lane;
-                const bool in_range = arow >= row_lo && arow < row_hi;
+        int stg = 0;
+        uint32_t in_par = 0;
+        uint32_t fl = FLUSH_IT;
+        for (uint32_t it = 0; it < niter; ++it, t += tstep) {
+            if (it < n_my) {
                 uint64_t code;
                 Counts r;
-                if (tma_tile(t)) {
+                if (t < t_full) {
                     mbar_wait(my_in + 8 * stg, in_par);
-                    const unsigned char* st = ring + stg * STAGE_BYTES;
-                    code = reinterpret_cast<const uint64_t*>(st)[lane];
+                    const uint32_t st = ring + stg * STAGE_BYTES;
+                    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(code) : "r"(st + lane * 8));
 #pragma unroll
-                    for (int b = 0; b < A1; ++b) r.c[b] = reinterpret_cast<const uint32_t*>(st + 256)[b * 32 + lane];
+                    for (int b = 0; b < A1; ++b)
+                        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(r.c[b]) : "r"(st + 256 + b * 128 + lane * 4));
                 } else {
-                    code = in_range ? __ldg(kmers + arow) : 0ull;
+                    const int64_t arow = a0 + (int64_t(t) << 5) + lane;
+                    const bool ok = arow < row_hi;
+                    code = ok ? __ldg(kmers + arow) : 0ull;
 #pragma unroll
-                    for (int b = 0; b < A1; ++b) r.c[b] = in_range ? __ldg(col + b * stride + arow) : 0u;
+                    for (int b = 0; b < A1; ++b) r.c[b] = ok ? __ldg(col + b * stride + arow) : 0u;
                 }
-                if (!in_range) {
-                    code = 0ull;
+                if (t == 0 || t >= t_full) {                 // only the first and the tail tile can hold rows outside the batch
+                    const int64_t arow = a0 + (int64_t(t) << 5) + lane;
+                    if (arow < row_lo || arow >= row_hi) {
 #pragma unroll
-                    for (int b = 0; b < A1; ++b) r.c[b] = 0u;
+                        for (int b = 0; b < A1; ++b) r.c[b] = 0u;
+                    }
                 }
                 r.cmax = max(max(max(r.c[0], r.c[1]), max(r.c[2], r.c[3])), r.c[4]);
                 if (r.cmax < (1u << 29))
@@ -248,119 +290,14 @@ linear_train_tc_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __res
                 const bool live = r.cmax != 0;              // zero-count row: ll = 0 and every gradient is 0
                 const uint32_t steps = warp_steps(live, r.cmax);   // (a warp collective: every lane has read its stage)
                 __syncwarp();
-                if (lane == 0) {                            // refill this stage with the tile of iteration it + nstage
-                    const int64_t t2 = tile_of(it + nstage, warp);
-                    if (it + nstage < niter && tma_tile(t2)) issue_tile(t2, stg);
-                }
+                if (lane < 6 && it + nstage < n_my && t + nstage * tstep < t_full)
+                    issue_tile(t + nstage * tstep, stg);     // refill this stage with the tile `nstage` iterations ahead
                 const int ns = int(code >> 58);
                 const uint64_t v = code & PAYLOAD_MASK;
-                // ---- head: product of chunk-table rows ----
-                double f[A1];
+                // ---- one-hot operand of the tile's tensor-core product (needs the k-mers only: written first, so that the
+                //      codes are dead while the float64 work runs) ----
+                if (it > 0) mbar_wait(bar_empty + 8 * warp, (it - 1) & 1u);   // the previous product has read the slab
                 {
-                    double p0 = 1.0, p1 = 1.0, p2 = 1.0, p3 = 1.0;
-                    int sh = 2 * lag, c0 = 0;
-                    for (int ch = 0; ch < nch; ++ch) {
-                        const int rr = ck.base + (ch < ck.extra ? 1 : 0);
-                        sh -= 2 * rr;
-                        int q = int(uint32_t(v >> sh) & ((1u << (2 * rr)) - 1u));
-                        if (ns > c0) q = ext_key(uint32_t(q), rr, ns - c0);
-                        c0 += rr;
-                        const int sw = half_swizzle(q);
-                        const double2 a = *reinterpret_cast<const double2*>(R + (ch * ENT + q) * 4 + sw);
-                        const double2 b = *reinterpret_cast<const double2*>(R + (ch * ENT + q) * 4 + (sw ^ 2));
-                        p0 *= a.x;
-                        p1 *= a.y;
-                        p2 *= b.x;
-                        p3 *= b.y;
-                    }
-                    const double z = 1.0 + ((p0 + p1) + (p2 + p3));
-                    if (z < 1e300 && z > 1e-300) {
-                        const double zi = 1.0 / z;
-                        f[0] = p0 * zi;
-                        f[1] = p1 * zi;
-                        f[2] = p2 * zi;
-                        f[3] = p3 * zi;
-                        f[4] = zi;
-                    } else {
-                        linear_head_exact(mat, code, lag, f);
-                    }
-                }
-                // ---- likelihood and its gradient with respect to the logits ----
-                double g[4], ll_row = 0.0;
-                {
-                    double add, prod, w[A1];
-                    if (TRAIN_AR) {
-                        double p[A1], ri[A1];
-#pragma unroll
-                        for (int b = 0; b < A1; ++b) p[b] = f[b] + BEAR_EPS;                 // bear_net.py:68
-                        mn_term(p, r, add, prod);
-                        inv5(p, ri);
-                        double u = 0.0;
-#pragma unroll
-                        for (int b = 0; b < A1; ++b) {
-                            w[b] = double(r.c[b]) * ri[b];                                   // d ll / d f_b
-                            u = fma(f[b], w[b], u);
-                        }
-#pragma unroll
-                        for (int b = 0; b < 4; ++b) g[b] = f[b] * (w[b] - u);
-                    } else {
-                        double conc[A1];
-#pragma unroll
-                        for (int b = 0; b < A1; ++b) conc[b] = fma(f[b], hinv, BEAR_EPS);       // bear_net.py:43
-                        letters_term<true>(stir, conc, r, steps, add, prod, w);
-                        double tadd, tdg;
-                        if (r.n < double(TABN)) {
-                            tadd = tab_lg[int(r.n)];
-                            tdg = tab_dg[int(r.n)];
-                        } else {
-                            double tprod;
-                            const double s = ((conc[0] + conc[1]) + (conc[2] + conc[3])) + conc[4];
-                            total_term<true>(s, r, tadd, tprod, tdg);
-                            tadd += log(tprod);
-                        }
-                        add -= tadd;
-                        // d ll/d conc_b = w_b - tdg; d ll/d f_b = that / h; softmax backward:
-                        // g_b = f_b (d ll/d f_b - sum_j f_j d ll/d f_j) = f_b (w_b - W) / h,  W = sum_j f_j w_j
-                        double W = 0.0;
-#pragma unroll
-                        for (int b = 0; b < A1; ++b) W = fma(f[b], w[b], W);
-                        if (live) dh_sum -= (W - tdg) * hinv;   // d ll / d h_signed = -sum_b f_b d ll/d f_b
-#pragma unroll
-                        for (int b = 0; b < 4; ++b) g[b] = f[b] * hinv * (w[b] - W);
-                    }
-                    if (live) {
-                        if (ll_out) {
-                            ll_row = add + log(prod);
-                            acc_add += ll_row;
-                        } else {
-                            acc_add += add;
-                            acc_prod.push(0.0, prod);
-                        }
-                    }
-                }
-                if (ll_out && in_range) ll_out[arow - row_lo] = ll_row;
-                // ---- fixed-point digits of the logit gradients: scale class from the largest |g| of the tile ----
-                uint32_t hmax = 0;
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    if (!live) g[b] = 0.0;
-                    hmax = max(hmax, uint32_t(__double2hiint(g[b])) & 0x7fffffffu);
-                }
-                hmax = __reduce_max_sync(0xffffffffu, hmax);
-                const int ex = int(hmax >> 20) - 1023;       // floor(log2 max|g|);  |g| <= row total < 2^35 by construction
-                const int cls = ex < 6 ? 0 : ex < 18 ? 1 : ex < 30 ? 2 : 3;
-                if (ex >= 42 && lane == 0) misc[2] = 1u;     // inf / nan (diverged parameters): the gradient is reported as nan
-                const double scale = __hiloint2double((1023 + 56 - 12 * cls) << 20, 0);
-                uint64_t z[4];
-#pragma unroll
-                for (int b = 0; b < 4; ++b)
-                    z[b] = (uint64_t(__double2ll_rn(g[b] * scale)) + DIGIT_BIAS) ^ DIGIT_BIAS;   // balanced base-256 digits
-                // ---- operands of the tile's tensor-core product ----
-                if (it > 0) mbar_wait(bar_empty + 8 * warp, uint32_t(it - 1) & 1u);   // the previous product has read the slab
-                {
-                    unsigned char* sb = smem_raw + L.slab_b + warp * SLAB_B + lane * 16;
-                    *reinterpret_cast<uint4*>(sb) = make_uint4(uint32_t(z[0]), uint32_t(z[0] >> 32), uint32_t(z[1]), uint32_t(z[1] >> 32));
-                    *reinterpret_cast<uint4*>(sb + 512) = make_uint4(uint32_t(z[2]), uint32_t(z[2] >> 32), uint32_t(z[3]), uint32_t(z[3] >> 32));
                     // one-hot rows m = 4 j + s (letters s of position j); the zero padding below the last position makes
                     // row 4 lag the all-rows row
                     const uint64_t vl = v << (64 - 2 * lag);
@@ -385,38 +322,183 @@ linear_train_tc_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __res
                     put_group(5, onehot_group<16>(xl));
                     put_group(6, onehot_group<8>(xl));
                     put_group(7, onehot_group<0>(xl));
-                    if (lane == 0) slab_cls[warp] = uint8_t(cls);
+                }
+                // ---- head: product of chunk-table rows (row = 32 bytes, halves swapped when bit 2 of the key is set) ----
+                double f[A1];
+                {
+                    double p0 = 1.0, p1 = 1.0, p2 = 1.0, p3 = 1.0;
+                    const uint64_t v5 = v << 5;
+#pragma unroll
+                    for (int ch = 0; ch < NCH; ++ch) {
+                        const int rr = hg.rr[ch];
+                        uint32_t q32 = uint32_t(v5 >> hg.sh[ch]) & (((1u << (2 * rr)) - 1u) << 5);     // 32 * key
+                        if (ns > hg.c0[ch]) q32 = uint32_t(ext_key(q32 >> 5, rr, ns - hg.c0[ch])) << 5;
+                        const uint32_t o = q32 | ((q32 >> 3) & 16u);
+                        const unsigned char* row = reinterpret_cast<const unsigned char*>(R) + ch * (ENT * 32);
+                        const double2 a = *reinterpret_cast<const double2*>(row + o);
+                        const double2 b = *reinterpret_cast<const double2*>(row + (o ^ 16u));
+                        p0 *= a.x;
+                        p1 *= a.y;
+                        p2 *= b.x;
+                        p3 *= b.y;
+                    }
+                    const double z = 1.0 + ((p0 + p1) + (p2 + p3));
+                    if (z < 1e300 && z > 1e-300) {
+                        const double zi = 1.0 / z;
+                        f[0] = p0 * zi;
+                        f[1] = p1 * zi;
+                        f[2] = p2 * zi;
+                        f[3] = p3 * zi;
+                        f[4] = zi;
+                    } else {
+                        linear_head_exact(mat, code, lag, f);
+                    }
+                }
+                // ---- likelihood and its gradient with respect to the logits ----
+                double g[4], ll_row = 0.0;
+                {
+                    double add, prod, w[A1];
+                    // (f is not kept across the lgamma / digamma work: f_b = p_b - eps resp. f_b / h = conc_b - eps recovers it to
+                    //  an ulp of the larger quantity, which is all the gradient needs)
+                    if (TRAIN_AR) {
+                        double p[A1], ri[A1];
+#pragma unroll
+                        for (int b = 0; b < A1; ++b) p[b] = f[b] + BEAR_EPS;                 // bear_net.py:68
+                        mn_term(p, r, add, prod);
+                        inv5(p, ri);
+                        double u = 0.0;
+#pragma unroll
+                        for (int b = 0; b < A1; ++b) {
+                            w[b] = double(r.c[b]) * ri[b];                                   // d ll / d f_b
+                            u = fma(p[b] - BEAR_EPS, w[b], u);
+                        }
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) g[b] = (p[b] - BEAR_EPS) * (w[b] - u);
+                    } else {
+                        double conc[A1];
+#pragma unroll
+                        for (int b = 0; b < A1; ++b) conc[b] = fma(f[b], hinv, BEAR_EPS);       // bear_net.py:43
+                        letters_term<true>(stir, conc, r, steps, add, prod, w);
+                        double tadd, tdg;
+                        if (r.n < double(TABN)) {
+                            tadd = tab_lg[int(r.n)];
+                            tdg = tab_dg[int(r.n)];
+                        } else {
+                            double tprod;
+                            const double s = ((conc[0] + conc[1]) + (conc[2] + conc[3])) + conc[4];
+                            total_term<true>(s, r, tadd, tprod, tdg);
+                            tadd += log(tprod);
+                        }
+                        add -= tadd;
+                        // d ll/d conc_b = w_b - tdg; d ll/d f_b = that / h; softmax backward:
+                        // g_b = f_b (d ll/d f_b - sum_j f_j d ll/d f_j) = (f_b / h) (w_b - W),  W = sum_j f_j w_j = h Wh
+                        double Wh = 0.0;
+#pragma unroll
+                        for (int b = 0; b < A1; ++b) Wh = fma(conc[b] - BEAR_EPS, w[b], Wh);
+                        if (live) dh_sum -= Wh - tdg * hinv;    // d ll / d h_signed = -sum_b f_b d ll/d f_b
+                        const double W = Wh * hval;
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) g[b] = (conc[b] - BEAR_EPS) * (w[b] - W);
+                    }
+                    if (live) {
+                        if (ll_out) {
+                            ll_row = add + log(prod);
+                            acc_add += ll_row;
+                        } else {
+                            acc_add += add;
+                            acc_prod.push(0.0, prod);
+                        }
+                    }
+                }
+                if (ll_out) {
+                    const int64_t arow = a0 + (int64_t(t) << 5) + lane;
+                    if (arow >= row_lo && arow < row_hi) ll_out[arow - row_lo] = ll_row;
+                }
+                // ---- fixed-point digits of the logit gradients: scale class from the largest |g| of the tile ----
+                uint32_t hmax = 0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    if (!live) g[b] = 0.0;
+                    hmax = max(hmax, uint32_t(__double2hiint(g[b])) & 0x7fffffffu);
+                }
+                hmax = __reduce_max_sync(0xffffffffu, hmax);
+                const int ex = int(hmax >> 20) - 1023;       // floor(log2 max|g|);  |g| <= row total < 2^35 by construction
+                const int cls = ex < 6 ? 0 : ex < 18 ? 1 : ex < 30 ? 2 : 3;
+                if (ex >= 42 && lane == 0) misc[2] = 1u;     // inf / nan (diverged parameters): the gradient is reported as nan
+                const double scale = __hiloint2double((1023 + 56 - 12 * cls) << 20, 0);
+                uint64_t z[4];
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    z[b] = (uint64_t(__double2ll_rn(g[b] * scale)) + DIGIT_BIAS) ^ DIGIT_BIAS;   // balanced base-256 digits
+                // ---- operands of the tile's tensor-core product ----
+                {
+                    unsigned char* sb = smem_raw + L.slab_b + warp * SLAB_B + lane * 16;
+                    *reinterpret_cast<uint4*>(sb) = make_uint4(uint32_t(z[0]), uint32_t(z[0] >> 32), uint32_t(z[1]), uint32_t(z[1] >> 32));
+                    *reinterpret_cast<uint4*>(sb + 512) = make_uint4(uint32_t(z[2]), uint32_t(z[2] >> 32), uint32_t(z[3]), uint32_t(z[3] >> 32));
                 }
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_full + 8 * warp);
+                if (lane == 0) {
+                    __threadfence_block();
+                    slab_status[warp] = uint8_t(((it + 1) << 2) | uint32_t(cls));
+                }
             }
             if (++stg == nstage) {
                 stg = 0;
                 in_par ^= 1u;
             }
-        } else if (lane == 0) {
-            // ---------------- tensor-core issuer: one product per staged tile, in warp order ----------------
-            const uint32_t idesc = umma_idesc_i8(128, 32);
-            for (int w = 0; w < T3_NPROD; ++w) {
-                if (tile_of(it, w) >= ntiles) break;
-                mbar_wait(bar_full + 8 * w, uint32_t(it) & 1u);
+            // read the accumulators back before a digit sum can leave 32 bits, and at the end
+            if (--fl == 0 || it + 1 == niter) {
+                fl = FLUSH_IT;
+                tc_fence_before();
+                __syncthreads();
                 tc_fence_after();
-                const uint32_t cls = slab_cls[w];
-                const uint64_t da = umma_desc(smem_u32(smem_raw + L.slab_a + w * SLAB_A), 128, 512);
-                const uint64_t db = umma_desc(smem_u32(smem_raw + L.slab_b + w * SLAB_B), 128, 512);
-                umma_i8(tmem + cls * 32, da, db, idesc, (cls_used >> cls) & 1u);
-                cls_used |= 1u << cls;
-                umma_commit(bar_empty + 8 * w);
+                flush_accumulators(tmem, misc[1], lag, acc, acc_start, ones);
+                tc_fence_before();
+                __syncthreads();
             }
         }
-        // ---------------- read the accumulators back before a digit sum can leave 32 bits, and at the end ----------------
-        if ((it + 1) % FLUSH_IT == 0 || it + 1 == niter) {
-            if (!producer && lane == 0) {
+    } else {
+        // ---------------- tensor-core issuer: one product per staged tile, whichever warp is ready ----------------
+        const uint32_t idesc = umma_idesc_i8(128, 32);
+        const uint64_t desc_a0 = umma_desc(smem_u32(smem_raw + L.slab_a), 128, 512);
+        const uint64_t desc_b0 = umma_desc(smem_u32(smem_raw + L.slab_b), 128, 512);
+        const uint32_t status_addr = smem_u32(smem_raw + L.misc + 16);
+        uint32_t seen[4] = {0u, 0u, 0u, 0u};                // last status bytes acted upon
+        for (uint32_t it0 = 0; it0 < niter; it0 += FLUSH_IT) {
+            const uint32_t it1 = it0 + FLUSH_IT < niter ? it0 + FLUSH_IT : niter;
+            if (lane == 0) {
+                uint32_t cls_used = 0;                      // accumulators written since the last read-back
+                // products still to issue in this window (only the very last iteration can be ragged)
+                uint32_t remaining = (it1 - it0) * T3_NPROD - (it1 == niter ? uint32_t(T3_NPROD - nlast) : 0u);
+                while (remaining) {
+                    uint32_t cur[4];
+                    asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(cur[0]), "=r"(cur[1]), "=r"(cur[2]), "=r"(cur[3]) : "r"(status_addr) : "memory");
+                    if (((cur[0] ^ seen[0]) | (cur[1] ^ seen[1]) | (cur[2] ^ seen[2]) | (cur[3] ^ seen[3])) == 0u) {
+                        __nanosleep(64);
+                        continue;
+                    }
+                    __threadfence_block();                  // the status bytes were written after the slabs
+                    tc_fence_after();
+#pragma unroll
+                    for (int w = 0; w < T3_NPROD; ++w) {
+                        const uint32_t st = (cur[w >> 2] >> (8 * (w & 3))) & 0xffu;
+                        if (st != ((seen[w >> 2] >> (8 * (w & 3))) & 0xffu)) {
+                            const uint32_t cls = st & 3u;
+                            umma_i8(tmem + cls * 32, desc_a0 + uint64_t(w * (SLAB_A >> 4)), desc_b0 + uint64_t(w * (SLAB_B >> 4)), idesc,
+                                    (cls_used >> cls) & 1u);
+                            cls_used |= 1u << cls;
+                            umma_commit(bar_empty + 8 * w);
+                            --remaining;
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) seen[i] = cur[i];
+                }
                 umma_commit(bar_done);
                 mbar_wait(bar_done, flushes & 1u);
                 misc[1] = cls_used;
-                cls_used = 0;
             }
             ++flushes;
             tc_fence_before();
@@ -427,7 +509,6 @@ linear_train_tc_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __res
             __syncthreads();
         }
     }
-
     if (warp == T3_NPROD) tmem_dealloc(tmem, TMEM_COLS);
     const int P = 2 + lag * A1 * A1;
     double* out = partials + int64_t(blockIdx.x) * P;
@@ -448,6 +529,27 @@ linear_train_tc_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __res
         const double val = b < 4 ? src[b] : -((src[0] + src[1]) + (src[2] + src[3]));
         out[2 + idx] = bad ? nan("") : val;
     }
+}
+
+template <bool TRAIN_AR, int NCH>
+int launch_train(int grid, size_t smem, cudaStream_t st, const uint64_t* km, const uint32_t* col, int64_t stride, int64_t lo,
+                 int64_t hi, int lag, const ChunkKeys& ck, const HeadGeom& hg, int nstage, int use_tma, const double* mat,
+                 const double* hs, double* ll, double* ws) {
+    BEAR_CUDA_CHECK(cudaFuncSetAttribute(linear_train_tc_kernel<TRAIN_AR, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    linear_train_tc_kernel<TRAIN_AR, NCH><<<grid, T3_THREADS, smem, st>>>(km, col, stride, lo, hi, lag, ck, hg, nstage, use_tma, mat, hs, ll, ws);
+    return 0;
+}
+
+template <bool TRAIN_AR>
+int launch_train_nch(int nch, int grid, size_t smem, cudaStream_t st, const uint64_t* km, const uint32_t* col, int64_t stride,
+                     int64_t lo, int64_t hi, int lag, const ChunkKeys& ck, const HeadGeom& hg, int nstage, int use_tma,
+                     const double* mat, const double* hs, double* ll, double* ws) {
+    switch (nch) {
+#define BEAR_CASE(N) case N: return launch_train<TRAIN_AR, N>(grid, smem, st, km, col, stride, lo, hi, lag, ck, hg, nstage, use_tma, mat, hs, ll, ws);
+        BEAR_CASE(1) BEAR_CASE(2) BEAR_CASE(3) BEAR_CASE(4) BEAR_CASE(5) BEAR_CASE(6) BEAR_CASE(7) BEAR_CASE(8)
+#undef BEAR_CASE
+    }
+    return BEAR_ERR_ARG;
 }
 
 }  // namespace
@@ -484,15 +586,18 @@ extern "C" int bear_linear_train_step(const uint64_t* d_kmers, const uint32_t* d
     const int64_t ntiles = (row0 + n - a0 + 31) / 32;
     const int64_t want = (ntiles + T3_NPROD - 1) / T3_NPROD;
     const int grid = int(want < 148 ? want : 148);
-    if (train_ar) {
-        BEAR_CUDA_CHECK(cudaFuncSetAttribute(linear_train_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        linear_train_tc_kernel<true><<<grid, T3_THREADS, smem, st>>>(d_kmers, d_col, stride, row0, row0 + n, lag, ck, nstage, use_tma,
-                                                                    d_mat, d_h_signed, d_ll_out, d_workspace);
-    } else {
-        BEAR_CUDA_CHECK(cudaFuncSetAttribute(linear_train_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        linear_train_tc_kernel<false><<<grid, T3_THREADS, smem, st>>>(d_kmers, d_col, stride, row0, row0 + n, lag, ck, nstage, use_tma,
-                                                                     d_mat, d_h_signed, d_ll_out, d_workspace);
+    HeadGeom hg;
+    for (int ch = 0; ch < 8; ++ch) {
+        const ChunkGeom cg = chunk_geom(lag, nch, ch < nch ? ch : nch - 1);
+        hg.rr[ch] = uint8_t(cg.size);
+        hg.c0[ch] = uint8_t(cg.start);
+        hg.sh[ch] = uint8_t(2 * (lag - cg.start - cg.size));
     }
+    const int rc = train_ar ? launch_train_nch<true>(nch, grid, smem, st, d_kmers, d_col, stride, row0, row0 + n, lag, ck, hg, nstage,
+                                                     use_tma, d_mat, d_h_signed, d_ll_out, d_workspace)
+                            : launch_train_nch<false>(nch, grid, smem, st, d_kmers, d_col, stride, row0, row0 + n, lag, ck, hg, nstage,
+                                                      use_tma, d_mat, d_h_signed, d_ll_out, d_workspace);
+    if (rc) return rc;
     BEAR_LAUNCH_CHECK("linear_train_tc_kernel");
     reduce_partials_kernel<<<(P + 127) / 128, 128, 0, st>>>(d_workspace, grid, P, -scale, d_flat);
     BEAR_LAUNCH_CHECK("reduce_partials_kernel");

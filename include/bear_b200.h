@@ -59,6 +59,7 @@ enum {
 
 const char* bear_last_error(void);
 int bear_version(void);                       /* ABI version, currently 1 */
+const char* bear_build_digest(void);          /* sha256 of the sources + compiler flags this binary was built from */
 int bear_alphabet_size(int alphabet);         /* 4 / 4 / 20 */
 int bear_max_lag(int alphabet);               /* 29 / 29 / 12 */
 
