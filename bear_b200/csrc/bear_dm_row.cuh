@@ -56,6 +56,28 @@ static __constant__ double kStirling[(SMALLC + 1) * (SMALLC + 1)] = {
 template <bool GRAD, typename TS>
 __device__ __forceinline__ void rf_letters(const TS* __restrict__ stir, const double (&a)[A1], const uint32_t (&c)[A1],
                                            uint32_t steps, double (&P)[A1], double (&D)[A1]) {
+    if (GRAD) {
+        // with derivatives (training): predicated products (a)(a+1)...(a+c-1) -- no shared-memory traffic, no float -> double
+        // conversions; measured 2 % faster than the polynomial form below, which stays for the evaluation (5 % faster there)
+        (void)stir;
+#pragma unroll
+        for (int b = 0; b < A1; ++b) {
+            P[b] = 1.0;
+            D[b] = 0.0;
+        }
+        double kd = 0.0;
+        for (uint32_t k = 0; k < steps; ++k, kd += 1.0) {
+#pragma unroll
+            for (int b = 0; b < A1; ++b) {
+                const double t = a[b] + kd;
+                if (c[b] > k) {
+                    D[b] = fma(D[b], t, P[b]);
+                    P[b] *= t;
+                }
+            }
+        }
+        return;
+    }
     const TS* row[A1];     // TS = float (exact: coefficients <= 13132) halves the shared-memory traffic, double saves the conversion
 #pragma unroll
     for (int b = 0; b < A1; ++b) {

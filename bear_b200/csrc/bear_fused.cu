@@ -1,7 +1,6 @@
-// Fused packed-path kernels (DNA/RNA, A1 = 5): the count-streaming hot path.
-//   linear_train2_kernel  bear_net._train_step (bear_net.py:146-197) + ar_funcs.make_ar_func_linear
-//                         (ar_funcs.py:23-46) + core.*.counts_log_prob (core.py:73-74,138-139), fwd+bwd
-//   explicit_train_kernel the same loss for a caller-evaluated head f (bear_ref / plugins)
+// Fused packed-path kernels (DNA/RNA, A1 = 5): the count-streaming hot path next to the training step
+// (bear_train.cu: linear_train_tc_kernel).
+//   explicit_train_kernel the training loss for a caller-evaluated head f (bear_ref / plugins)
 //   eval_kernel           bear_net._evaluation_step (bear_net.py:323-371), h_scan (bear_net.py:516-531)
 //   bmm_kernel            dataloader._marginal_step (dataloader.py:111-113)
 // Every kernel streams the packed table once (8 B k-mer + 20 B per count column per row) and keeps all
@@ -12,10 +11,7 @@
 //     predicated straight-line code; terms that do not depend on the row's k-mer (the "total" term of
 //     the Dirichlet-multinomial, BMM priors) come from per-CTA tables indexed by the count;
 //   * log() is taken of running products spanning many rows, not once per row; the five reciprocals
-//     of a row share one division;
-//   * the weight-table gradient is scattered without atomics: producer warps stage rows in shared memory,
-//     each gradient chunk table is owned by one consumer warp, rows with equal keys are ranked by the
-//     producer (match.any) and applied in separate read-modify-write rounds.
+//     of a row share one division.
 // Reductions are two-stage and deterministic across CTAs: per-CTA partials in the caller's workspace,
 // then a fixed-order sum.
 #include <math.h>
@@ -99,357 +95,6 @@ __device__ __forceinline__ int noisy_argmax5(const double (&v)[A1], double sigma
 #pragma unroll
     for (int b = 0; b < A1; ++b) x.v[b] = v[b];
     return argmax_tiebreak(x, top, thr, near == exact, exact, sigma, seed, row, model);
-}
-
-// ------------------------------------------------------------------------------------------------
-// linear head, fused forward + backward, v2: warp-specialised, barrier-light
-// ------------------------------------------------------------------------------------------------
-// One CTA of 16 warps per SM.  Warps 0..nch-1 are CONSUMERS: warp ch owns the gradient chunk table G[ch] and
-// does nothing but scatter staged rows into it.  The other warps are PRODUCERS: each computes TPW tiles of
-// 32 rows per iteration (decode -> table-gather head -> Dirichlet-multinomial forward/backward) and stages,
-// per row, the four logit gradients and the row's key into every chunk table.  The stage is double
-// buffered, so one __syncthreads per iteration is enough: consumers scatter iteration i-1 while producers
-// compute iteration i.  The loads of a producer's next tile are issued before the current tile is computed.
-//
-// Start symbols only occur as a prefix run (summarize.py:441-443), so the chunk tables carry, next to the 4^r
-// plain symbol combinations of a chunk of r positions, the sum_{s=1..r} 4^(r-s) patterns with s leading
-// starts (<= 85): every k-mer takes the table path, there is no per-position side path and no atomics.
-constexpr int T2_THREADS = 512;
-constexpr int T2_NW = T2_THREADS / 32;
-// G[q] += (s0, s1, s2, s3): plain read-modify-write of one 32-byte table row (two 128-bit accesses)
-__device__ __forceinline__ void rmw_row(double* Gc, int q, double s0, double s1, double s2, double s3) {
-    const int sw = half_swizzle(q);
-    double2* lo = reinterpret_cast<double2*>(Gc + q * 4 + sw);
-    double2* hi = reinterpret_cast<double2*>(Gc + q * 4 + (sw ^ 2));
-    double2 a = *lo, b = *hi;
-    a.x += s0;
-    a.y += s1;
-    b.x += s2;
-    b.y += s3;
-    *lo = a;
-    *hi = b;
-}
-
-// Kernel experiments, compiled in with BEAR_NVCC_EXTRA=-DBEAR_TRAIN_EXPERIMENTS (bear_b200/build.py): with
-// BEAR_TRAIN_DEBUG=1 in the environment the consumers skip the scatter -- wrong results, timing of the producer side
-// only (tools/ab_train.py; profiles/README.md "Experiments")
-#ifdef BEAR_TRAIN_EXPERIMENTS
-__constant__ int g_train_debug = 0;
-// [0] cycles the producer warps spent computing (summed over warps and CTAs), [1] the same for the consumer warps'
-// scatter, [2] cycles between the first and the last barrier summed over CTAs, [3] producer warps, [4] consumer warps:
-// busy fraction of a role = [0 or 1] / ([2] * warps of that role per CTA)
-__device__ unsigned long long g_train_cycles[5];
-#define BEAR_TRAIN_SKIP_SCATTER (g_train_debug != 0)
-#define BEAR_TRAIN_CLOCK() clock64()
-#else
-#define BEAR_TRAIN_SKIP_SCATTER false
-#define BEAR_TRAIN_CLOCK() 0ll
-#endif
-
-struct Train2Layout {                // offsets in bytes from the start of dynamic shared memory
-    int R, G, stage_g, stage_q, stage_m, tags, symtab, tab_lg, tab_dg, stir, red, total;
-};
-
-__host__ __device__ inline Train2Layout train2_layout(int nch, int tpw) {
-    const int tiles = (T2_NW - nch) * tpw;
-    Train2Layout L;
-    int o = 0;
-    L.R = o;        o += nch * ENT * 4 * 8;
-    L.G = o;        o += nch * ENT * 4 * 8;
-    L.stage_g = o;  o += 2 * tiles * 4 * 32 * 8;           // [buf][tile][letter][lane] double
-    L.stage_q = o;  o += 2 * tiles * nch * 32 * 2;         // [buf][tile][chunk][lane] uint16
-    L.stage_m = o;  o += ((2 * tiles * 4 + 15) / 16) * 16; // [buf][tile] uint32 live-row masks
-    L.tags = o;     o += ((2 * tiles * nch + 15) / 16) * 16; // [buf][tile][chunk] uint8: largest rank of a row among its key's rows
-    L.symtab = o;   o += 2 * ENT * 2;                      // [size class][entry] packed symbols
-    L.tab_lg = o;   o += TABN * 8;
-    L.tab_dg = o;   o += TABN * 8;
-    L.stir = o;     o += STIR_N * 8;
-    L.red = o;      o += 32 * 8;
-    L.total = o;
-    return L;
-}
-
-template <bool TRAIN_AR>
-__global__ void __launch_bounds__(T2_THREADS, 1)
-linear_train2_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ col, int64_t stride,
-                     int64_t n, int lag, const ChunkKeys ck, int tpw, const double* __restrict__ mat,
-                     const double* __restrict__ h_signed, double* __restrict__ ll_out, double* __restrict__ partials) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int nch = num_chunks(lag);
-    const Train2Layout L = train2_layout(nch, tpw);
-    double* R = reinterpret_cast<double*>(smem_raw + L.R);                // [nch][ENT][4] forward ratios
-    double* G = reinterpret_cast<double*>(smem_raw + L.G);                // [nch][ENT][4] d ll / d chunk logits
-    double* stage_g = reinterpret_cast<double*>(smem_raw + L.stage_g);
-    uint16_t* stage_q = reinterpret_cast<uint16_t*>(smem_raw + L.stage_q);
-    uint32_t* stage_m = reinterpret_cast<uint32_t*>(smem_raw + L.stage_m);
-    uint8_t* stage_r = smem_raw + L.tags;
-    uint16_t* symtab = reinterpret_cast<uint16_t*>(smem_raw + L.symtab);
-    double* tab_lg = reinterpret_cast<double*>(smem_raw + L.tab_lg);
-    double* tab_dg = reinterpret_cast<double*>(smem_raw + L.tab_dg);
-    float* stir = reinterpret_cast<float*>(smem_raw + L.stir);
-    double* red = reinterpret_cast<double*>(smem_raw + L.red);
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int tiles = (T2_NW - nch) * tpw;                  // tiles staged per iteration
-    const double hinv = exp(-h_signed[0]);                  // 1 / h,  h = exp(h_signed)  (bear_net.py:186)
-
-    // ---------------- tables ----------------
-    for (int i = threadIdx.x; i < nch * ENT * 4; i += blockDim.x) G[i] = 0.0;
-    for (int i = threadIdx.x; i < STIR_N; i += blockDim.x) stir[i] = float(kStirling[i]);
-    for (int i = threadIdx.x; i < 2 * tiles; i += blockDim.x) stage_m[i] = 0u;
-    if (!TRAIN_AR && threadIdx.x < TABN) {
-        // the concentrations of a row sum to 1/h + 5 eps whatever its k-mer (softmax sums to 1)
-        const LgDg t = lgdg_diff<true>(hinv + A1 * BEAR_EPS, double(threadIdx.x));
-        tab_lg[threadIdx.x] = t.add + (t.mul == 1.0 ? 0.0 : log(t.mul));
-        tab_dg[threadIdx.x] = t.dg;
-    }
-    build_ext_tables(mat, R, symtab, lag, ck);
-    __syncthreads();
-
-    double acc_add = 0.0, dh_sum = 0.0;
-    LogProdLong acc_prod;
-    const int64_t ntiles = (n + 31) >> 5;
-    const int64_t per_iter = int64_t(gridDim.x) * tiles;
-    const int64_t niter = (ntiles + per_iter - 1) / per_iter;
-    const bool producer = warp >= nch;
-    const int slot0 = (warp - nch) * tpw;                   // this producer's first stage slot
-
-    // tile of (iteration it, slot s): consecutive CTAs take consecutive blocks of `tiles` tiles
-    auto tile_of = [&](int64_t it, int s) { return (it * gridDim.x + blockIdx.x) * tiles + s; };
-
-    RowIn nxt;
-    if (producer) nxt = load_row(kmers, col, stride, (tile_of(0, slot0) << 5) + lane, niter > 0 ? n : 0);
-
-    long long busy = 0;
-    const long long t_begin = BEAR_TRAIN_CLOCK();
-    for (int64_t it = 0; it <= niter; ++it) {
-        const int buf = int(it & 1);
-        const long long t_it = BEAR_TRAIN_CLOCK();
-        if (producer) {
-            if (it < niter) {
-                for (int k = 0; k < tpw; ++k) {
-                    const int slot = slot0 + k;
-                    const int64_t i = (tile_of(it, slot) << 5) + lane;
-                    const RowIn cur = nxt;
-                    {   // prefetch the next tile of this warp (next slot, or the first slot of the next iteration)
-                        const bool last = k + 1 == tpw;
-                        const int64_t ti = last ? tile_of(it + 1, slot0) : tile_of(it, slot + 1);
-                        nxt = load_row(kmers, col, stride, (ti << 5) + lane, (last && it + 1 >= niter) ? 0 : n);
-                    }
-                    Counts r;
-#pragma unroll
-                    for (int b = 0; b < A1; ++b) r.c[b] = cur.c[b];
-                    r.cmax = max(max(max(r.c[0], r.c[1]), max(r.c[2], r.c[3])), r.c[4]);
-                    if (r.cmax < (1u << 29))
-                        r.n = double((r.c[0] + r.c[1]) + (r.c[2] + r.c[3]) + r.c[4]);
-                    else
-                        r.n = (double(r.c[0]) + double(r.c[1])) + (double(r.c[2]) + double(r.c[3])) + double(r.c[4]);
-                    const bool in_range = i < n;
-                    const bool live = r.cmax != 0;          // zero-count row: ll = 0 and every gradient is 0
-                    const uint32_t steps = warp_steps(live, r.cmax);
-                    // ---- head: product of chunk-table rows; the keys are staged for the consumers ----
-                    double f[A1];
-                    {
-                        const int ns = int(cur.code >> 58);
-                        const uint64_t v = cur.code & PAYLOAD_MASK;
-                        uint16_t* sq = stage_q + ((buf * tiles + slot) * nch) * 32 + lane;
-                        double p0 = 1.0, p1 = 1.0, p2 = 1.0, p3 = 1.0;
-                        int sh = 2 * lag, c0 = 0;
-                        for (int ch = 0; ch < nch; ++ch) {
-                            const int rr = ck.base + (ch < ck.extra ? 1 : 0);
-                            sh -= 2 * rr;
-                            int q = int(uint32_t(v >> sh) & ((1u << (2 * rr)) - 1u));
-                            if (ns > c0) q = ext_key(uint32_t(q), rr, ns - c0);
-                            c0 += rr;
-                            // rank of this row among the tile's rows with the same key: consumers apply rank 0 rows,
-                            // then rank 1 rows, ... so equal keys never meet in one read-modify-write round
-                            // (match.any is slow: the table gather below is issued before its result is used)
-                            const unsigned grp = __match_any_sync(0xffffffffu, live ? q : 0x10000 + lane);
-                            const int sw = half_swizzle(q);
-                            const double2 a = *reinterpret_cast<const double2*>(R + (ch * ENT + q) * 4 + sw);
-                            const double2 b = *reinterpret_cast<const double2*>(R + (ch * ENT + q) * 4 + (sw ^ 2));
-                            p0 *= a.x;
-                            p1 *= a.y;
-                            p2 *= b.x;
-                            p3 *= b.y;
-                            const int rank = __popc(grp & ((1u << lane) - 1u));
-                            const int maxr = __reduce_max_sync(0xffffffffu, live ? rank : 0);
-                            sq[ch * 32] = uint16_t(q | (rank << 10));
-                            if (lane == 0) stage_r[(buf * tiles + slot) * nch + ch] = uint8_t(maxr);
-                        }
-                        const double z = 1.0 + ((p0 + p1) + (p2 + p3));
-                        if (z < 1e300 && z > 1e-300) {
-                            const double zi = 1.0 / z;
-                            f[0] = p0 * zi;
-                            f[1] = p1 * zi;
-                            f[2] = p2 * zi;
-                            f[3] = p3 * zi;
-                            f[4] = zi;
-                        } else {
-                            linear_head_exact(mat, cur.code, lag, f);
-                        }
-                    }
-                    double g[A1] = {0, 0, 0, 0, 0}, ll_row = 0.0;
-                    {
-                        double add, prod, w[A1];
-                        if (TRAIN_AR) {
-                            double p[A1], ri[A1];
-#pragma unroll
-                            for (int b = 0; b < A1; ++b) p[b] = f[b] + BEAR_EPS;                 // bear_net.py:68
-                            mn_term(p, r, add, prod);
-                            inv5(p, ri);
-                            double u = 0.0;
-#pragma unroll
-                            for (int b = 0; b < A1; ++b) {
-                                w[b] = double(r.c[b]) * ri[b];                                   // d ll / d f_b
-                                u = fma(f[b], w[b], u);
-                            }
-#pragma unroll
-                            for (int b = 0; b < A1; ++b) g[b] = f[b] * (w[b] - u);
-                        } else {
-                            double conc[A1];
-#pragma unroll
-                            for (int b = 0; b < A1; ++b) conc[b] = fma(f[b], hinv, BEAR_EPS);       // bear_net.py:43
-                            letters_term<true>(stir, conc, r, steps, add, prod, w);
-                            double tadd, tdg;
-                            if (r.n < double(TABN)) {
-                                tadd = tab_lg[int(r.n)];
-                                tdg = tab_dg[int(r.n)];
-                            } else {
-                                double tprod;
-                                const double s = ((conc[0] + conc[1]) + (conc[2] + conc[3])) + conc[4];
-                                total_term<true>(s, r, tadd, tprod, tdg);
-                                tadd += log(tprod);
-                            }
-                            add -= tadd;
-                            // d ll/d conc_b = w_b - tdg; d ll/d f_b = that / h; softmax backward:
-                            // g_b = f_b (d ll/d f_b - sum_j f_j d ll/d f_j) = f_b (w_b - W) / h,  W = sum_j f_j w_j
-                            double W = 0.0;
-#pragma unroll
-                            for (int b = 0; b < A1; ++b) W = fma(f[b], w[b], W);
-                            if (live) dh_sum -= (W - tdg) * hinv;   // d ll / d h_signed = -sum_b f_b d ll/d f_b
-#pragma unroll
-                            for (int b = 0; b < A1; ++b) g[b] = f[b] * hinv * (w[b] - W);
-                        }
-                        if (live) {
-                            if (ll_out) {
-                                ll_row = add + log(prod);
-                                acc_add += ll_row;
-                            } else {
-                                acc_add += add;
-                                acc_prod.push(0.0, prod);
-                            }
-                        }
-                    }
-                    if (ll_out && in_range) ll_out[i] = ll_row;
-                    double* sg = stage_g + ((buf * tiles + slot) * 4) * 32 + lane;
-#pragma unroll
-                    for (int b = 0; b < 4; ++b) sg[b * 32] = g[b];
-                    const unsigned m = __ballot_sync(0xffffffffu, live);
-                    if (lane == 0) stage_m[buf * tiles + slot] = m;
-                }
-            }
-        } else if (it > 0) {
-            // ---------------- consumer: warp ch scatters chunk ch of every tile staged in iteration it-1 --------
-            // Rows with equal keys would collide on one table entry.  The producer ranked every row among the rows of
-            // its tile with the same key, so round r applies the rank-r rows with plain read-modify-writes: distinct
-            // keys within a round, no atomics, no retry loop (random 256-key chunks need 2 rounds 6 times out of 7).
-            // Keys with more than five rows in a tile (the leading chunks of a table sorted by k-mer) have their
-            // remaining rows summed with a butterfly first.
-            const int pb = buf ^ 1;
-            const int ch = warp;
-            double* Gc = G + ch * ENT * 4;
-            const uint32_t* sm = stage_m + pb * tiles;
-            const uint8_t* sr = stage_r + pb * tiles * nch + ch;
-            const uint16_t* sq = stage_q + (pb * tiles * nch + ch) * 32 + lane;
-            const double* sg = stage_g + pb * tiles * 4 * 32;
-            // the staged row of the next tile is fetched while the current one is scattered
-            unsigned m_n = sm[0];
-            int q_n = int(*sq), r_n = int(*sr);
-            double n0 = sg[lane], n1 = sg[32 + lane], n2 = sg[64 + lane], n3 = sg[96 + lane];
-            for (int t = 0; t < tiles; ++t, sq += nch * 32, sg += 4 * 32, sr += nch) {
-                const unsigned m = m_n;
-                const bool pend = (m >> lane) & 1u;
-                const int q = q_n & 1023, rank = q_n >> 10, rounds = r_n;
-                double s0 = n0, s1 = n1, s2 = n2, s3 = n3;
-                if (t + 1 < tiles) {
-                    m_n = sm[t + 1];
-                    q_n = int(sq[nch * 32]);
-                    r_n = int(sr[nch]);
-                    n0 = sg[128 + lane];
-                    n1 = sg[160 + lane];
-                    n2 = sg[192 + lane];
-                    n3 = sg[224 + lane];
-                }
-                if (m == 0u || BEAR_TRAIN_SKIP_SCATTER) continue;
-                bool todo = pend;
-                int plain = rounds;
-                if (rounds > 4) {
-                    // keys with more than five rows in the tile (at most five such keys; the rule for the leading
-                    // chunks of a table sorted by k-mer): all rows of such a key are summed with a butterfly and
-                    // applied by the key's rank-5 lane
-                    unsigned heads = __ballot_sync(0xffffffffu, pend && rank == 5);
-                    while (heads) {
-                        const int L = __ffs(heads) - 1;
-                        heads &= heads - 1;
-                        const int qL = __shfl_sync(0xffffffffu, q, L);       // every lane takes part in the shuffle
-                        const bool mem = pend && q == qL;
-                        const double t0 = warp_sum(mem ? s0 : 0.0), t1 = warp_sum(mem ? s1 : 0.0);
-                        const double t2 = warp_sum(mem ? s2 : 0.0), t3 = warp_sum(mem ? s3 : 0.0);
-                        if (lane == L) rmw_row(Gc, q, t0, t1, t2, t3);
-                        todo = todo && !mem;
-                    }
-                    __syncwarp();
-                    plain = __any_sync(0xffffffffu, todo) ? 4 : -1;      // the other keys have at most five rows each
-                }
-                for (int r = 0; r <= plain; ++r) {
-                    if (todo && rank == r) rmw_row(Gc, q, s0, s1, s2, s3);
-                    __syncwarp();
-                }
-            }
-        }
-        busy += BEAR_TRAIN_CLOCK() - t_it;
-        __syncthreads();
-    }
-#ifdef BEAR_TRAIN_EXPERIMENTS
-    if (lane == 0) {
-        atomicAdd(&g_train_cycles[producer ? 0 : 1], (unsigned long long)busy);
-        atomicAdd(&g_train_cycles[producer ? 3 : 4], 1ull);
-        if (threadIdx.x == 0) atomicAdd(&g_train_cycles[2], (unsigned long long)(clock64() - t_begin));
-    }
-#else
-    (void)busy;
-    (void)t_begin;
-#endif
-
-    const int P = 2 + lag * A1 * A1;
-    double* out = partials + int64_t(blockIdx.x) * P;
-    const double ll_thread = acc_add + acc_prod.value();
-    const double ll_blk = block_sum(ll_thread, red);
-    const double dh_blk = block_sum(dh_sum, red);
-    if (threadIdx.x == 0) {
-        out[0] = ll_blk;
-        out[1] = dh_blk;
-    }
-    __syncthreads();
-    // marginalise the chunk-table gradients back onto mat[j, s, b] (s = 4: the start symbol)
-    for (int idx = threadIdx.x; idx < lag * A1 * A1; idx += blockDim.x) {
-        const int b = idx % A1, s = (idx / A1) % A1, j = idx / (A1 * A1);
-        int ch = 0;
-        ChunkGeom cg = chunk_geom(lag, nch, 0);
-        while (j >= cg.start + cg.size) cg = chunk_geom(lag, nch, ++ch);
-        const int p = j - cg.start;
-        const uint16_t* st = symtab + (ch < ck.extra ? 0 : ENT);
-        const int ne = ext_entries(cg.size);
-        double acc = 0.0;
-        for (int e = 0; e < ne; ++e) {
-            if (int((st[e] >> (3 * p)) & 7u) != s) continue;
-            const double* src = G + (ch * ENT + e) * 4;
-            if (b < 4) acc += src[((b & 2) ^ half_swizzle(e)) + (b & 1)];
-            else acc -= (src[0] + src[1]) + (src[2] + src[3]);   // the 5 logit gradients sum to 0
-        }
-        out[2 + idx] = acc;
-    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -955,54 +600,6 @@ int launch_eval_nm(bool small, bool has_train, int grid, size_t smem, cudaStream
 }
 
 }  // namespace
-
-#ifdef BEAR_TRAIN_EXPERIMENTS
-// reads and clears the cycle counters of linear_train2_kernel (synchronises the device)
-extern "C" int bear_debug_train_cycles(unsigned long long* out5) {
-    BEAR_CUDA_CHECK(cudaDeviceSynchronize());
-    BEAR_CUDA_CHECK(cudaMemcpyFromSymbol(out5, g_train_cycles, 5 * sizeof(unsigned long long)));
-    const unsigned long long zero[5] = {0, 0, 0, 0, 0};
-    BEAR_CUDA_CHECK(cudaMemcpyToSymbol(g_train_cycles, zero, sizeof(zero)));
-    return BEAR_OK;
-}
-#endif
-
-extern "C" int bear_linear_train_step_legacy(const uint64_t* d_kmers, const uint32_t* d_col, int64_t stride,
-                                      int64_t row0, int64_t n, int lag, const double* d_mat,
-                                      const double* d_h_signed, double scale, int train_ar,
-                                      double* d_flat, double* d_ll_out, double* d_workspace, void* stream) {
-    const char* fn = "bear_linear_train_step";
-    BEAR_REQUIRE(d_kmers && d_col && d_mat && d_h_signed && d_flat && d_workspace, fn);
-    BEAR_REQUIRE(n >= 0 && row0 >= 0 && stride >= row0 + n, fn);
-    BEAR_REQUIRE(lag >= 1 && lag <= 29, fn);
-    if (n == 0) return BEAR_OK;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int P = 2 + lag * A1 * A1;
-    const ChunkKeys ck = make_chunk_keys(lag);
-    const int nch = num_chunks(lag);
-    const int tpw = size_t(train2_layout(nch, 2).total) <= size_t(227 * 1024) ? 2 : 1;
-    const size_t smem2 = size_t(train2_layout(nch, tpw).total);
-    const int64_t ntiles = (n + 31) / 32, per_cta = int64_t(T2_NW - nch) * tpw;
-    const int64_t want = (ntiles + per_cta - 1) / per_cta;
-    const int grid2 = int(want < 148 ? want : 148);
-#ifdef BEAR_TRAIN_EXPERIMENTS
-    static const int debug = getenv("BEAR_TRAIN_DEBUG") ? atoi(getenv("BEAR_TRAIN_DEBUG")) : 0;
-    if (debug) BEAR_CUDA_CHECK(cudaMemcpyToSymbolAsync(g_train_debug, &debug, sizeof(int), 0, cudaMemcpyHostToDevice, st));
-#endif
-    if (train_ar) {
-        if (set_smem(linear_train2_kernel<true>, smem2)) return BEAR_ERR_CUDA;
-        linear_train2_kernel<true><<<grid2, T2_THREADS, smem2, st>>>(d_kmers + row0, d_col + row0, stride, n, lag, ck, tpw,
-                                                                    d_mat, d_h_signed, d_ll_out, d_workspace);
-    } else {
-        if (set_smem(linear_train2_kernel<false>, smem2)) return BEAR_ERR_CUDA;
-        linear_train2_kernel<false><<<grid2, T2_THREADS, smem2, st>>>(d_kmers + row0, d_col + row0, stride, n, lag, ck, tpw,
-                                                                     d_mat, d_h_signed, d_ll_out, d_workspace);
-    }
-    BEAR_LAUNCH_CHECK("linear_train2_kernel");
-    reduce_partials_kernel<<<(P + 127) / 128, 128, 0, st>>>(d_workspace, grid2, P, -scale, d_flat);
-    BEAR_LAUNCH_CHECK("reduce_partials_kernel");
-    return BEAR_OK;
-}
 
 extern "C" int bear_dm_train_step_explicit(const uint32_t* d_col, int64_t stride, int64_t row0, int64_t n,
                                            const double* d_f, const double* d_h_signed, double scale,

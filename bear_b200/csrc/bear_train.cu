@@ -68,7 +68,7 @@ __host__ __device__ constexpr Train3Layout train3_layout(int nch, int nstage) {
     L.symtab = o;     o += 2 * ENT * 2;
     L.red = o;        o += 32 * 8;
     L.bars = o;       o += (T3_NPROD + T3_NPROD * MAX_STAGES + 1) * 8;
-    L.misc = o;       o += 32;                   // [0] tmem base [1] classes in use [2] non-finite flag; +16: slab status bytes
+    L.misc = o;       o += 48;                   // [0] tmem base [1] classes in use [2] non-finite flag; +16: 32 slab status bytes
     o = (o + 127) & ~127;
     L.ring = o;       o += T3_NPROD * nstage * STAGE_BYTES;      // last: every other offset is independent of nstage
     L.total = o;
@@ -160,8 +160,13 @@ struct HeadGeom {
     uint8_t sh[8], rr[8], c0[8];
 };
 
+#ifdef BEAR_T3_MAXNREG
+#define BEAR_T3_BOUNDS __maxnreg__(BEAR_T3_MAXNREG)
+#else
+#define BEAR_T3_BOUNDS __launch_bounds__(T3_THREADS, 1)
+#endif
 template <bool TRAIN_AR, int NCH>
-__global__ void __launch_bounds__(T3_THREADS, 1)
+__global__ void BEAR_T3_BOUNDS
 linear_train_tc_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ col, int64_t stride, int64_t row_lo,
                        int64_t row_hi, int lag, const ChunkKeys ck, const HeadGeom hg, int nstage, int use_tma,
                        const double* __restrict__ mat, const double* __restrict__ h_signed, double* __restrict__ ll_out,
@@ -208,7 +213,7 @@ linear_train_tc_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __res
         mbar_fence_init();
         misc[1] = 0u;
         misc[2] = 0u;
-        for (int i = 4; i < 8; ++i) misc[i] = 0u;            // slab status bytes
+        for (int i = 4; i < 12; ++i) misc[i] = 0u;           // slab status bytes
     }
     if (warp == T3_NPROD) tmem_alloc(smem_u32(const_cast<uint32_t*>(&misc[0])), TMEM_COLS);
     build_ext_tables(mat, R, symtab, lag, ck);
@@ -294,35 +299,6 @@ linear_train_tc_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __res
                     issue_tile(t + nstage * tstep, stg);     // refill this stage with the tile `nstage` iterations ahead
                 const int ns = int(code >> 58);
                 const uint64_t v = code & PAYLOAD_MASK;
-                // ---- one-hot operand of the tile's tensor-core product (needs the k-mers only: written first, so that the
-                //      codes are dead while the float64 work runs) ----
-                if (it > 0) mbar_wait(bar_empty + 8 * warp, (it - 1) & 1u);   // the previous product has read the slab
-                {
-                    // one-hot rows m = 4 j + s (letters s of position j); the zero padding below the last position makes
-                    // row 4 lag the all-rows row
-                    const uint64_t vl = v << (64 - 2 * lag);
-                    const uint32_t xh = uint32_t(vl >> 32), xl = uint32_t(vl);
-                    const bool any_start = __any_sync(0xffffffffu, ns > 0);
-                    unsigned char* sa = smem_raw + L.slab_a + warp * SLAB_A + lane * 16;
-                    auto put_group = [&](int gI, uint4 w) {
-                        if (gI >= ngrp) return;
-                        if (any_start) {                     // positions under the start run select no letter
-                            if (ns > 4 * gI) w.x = 0u;
-                            if (ns > 4 * gI + 1) w.y = 0u;
-                            if (ns > 4 * gI + 2) w.z = 0u;
-                            if (ns > 4 * gI + 3) w.w = 0u;
-                        }
-                        *reinterpret_cast<uint4*>(sa + gI * 512) = w;
-                    };
-                    put_group(0, onehot_group<24>(xh));
-                    put_group(1, onehot_group<16>(xh));
-                    put_group(2, onehot_group<8>(xh));
-                    put_group(3, onehot_group<0>(xh));
-                    put_group(4, onehot_group<24>(xl));
-                    put_group(5, onehot_group<16>(xl));
-                    put_group(6, onehot_group<8>(xl));
-                    put_group(7, onehot_group<0>(xl));
-                }
                 // ---- head: product of chunk-table rows (row = 32 bytes, halves swapped when bit 2 of the key is set) ----
                 double f[A1];
                 {
@@ -431,6 +407,33 @@ linear_train_tc_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __res
                 for (int b = 0; b < 4; ++b)
                     z[b] = (uint64_t(__double2ll_rn(g[b] * scale)) + DIGIT_BIAS) ^ DIGIT_BIAS;   // balanced base-256 digits
                 // ---- operands of the tile's tensor-core product ----
+                if (it > 0) mbar_wait(bar_empty + 8 * warp, (it - 1) & 1u);   // the previous product has read the slab
+                {
+                    // one-hot rows m = 4 j + s (letters s of position j); the zero padding below the last position makes
+                    // row 4 lag the all-rows row
+                    const uint64_t vl = v << (64 - 2 * lag);
+                    const uint32_t xh = uint32_t(vl >> 32), xl = uint32_t(vl);
+                    const bool any_start = __any_sync(0xffffffffu, ns > 0);
+                    unsigned char* sa = smem_raw + L.slab_a + warp * SLAB_A + lane * 16;
+                    auto put_group = [&](int gI, uint4 w) {
+                        if (gI >= ngrp) return;
+                        if (any_start) {                     // positions under the start run select no letter
+                            if (ns > 4 * gI) w.x = 0u;
+                            if (ns > 4 * gI + 1) w.y = 0u;
+                            if (ns > 4 * gI + 2) w.z = 0u;
+                            if (ns > 4 * gI + 3) w.w = 0u;
+                        }
+                        *reinterpret_cast<uint4*>(sa + gI * 512) = w;
+                    };
+                    put_group(0, onehot_group<24>(xh));
+                    put_group(1, onehot_group<16>(xh));
+                    put_group(2, onehot_group<8>(xh));
+                    put_group(3, onehot_group<0>(xh));
+                    put_group(4, onehot_group<24>(xl));
+                    put_group(5, onehot_group<16>(xl));
+                    put_group(6, onehot_group<8>(xl));
+                    put_group(7, onehot_group<0>(xl));
+                }
                 {
                     unsigned char* sb = smem_raw + L.slab_b + warp * SLAB_B + lane * 16;
                     *reinterpret_cast<uint4*>(sb) = make_uint4(uint32_t(z[0]), uint32_t(z[0] >> 32), uint32_t(z[1]), uint32_t(z[1] >> 32));
@@ -464,7 +467,8 @@ linear_train_tc_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __res
         const uint64_t desc_a0 = umma_desc(smem_u32(smem_raw + L.slab_a), 128, 512);
         const uint64_t desc_b0 = umma_desc(smem_u32(smem_raw + L.slab_b), 128, 512);
         const uint32_t status_addr = smem_u32(smem_raw + L.misc + 16);
-        uint32_t seen[4] = {0u, 0u, 0u, 0u};                // last status bytes acted upon
+        constexpr int NSW = (T3_NPROD + 3) / 4;              // status words
+        uint32_t seen[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};   // last status bytes acted upon
         for (uint32_t it0 = 0; it0 < niter; it0 += FLUSH_IT) {
             const uint32_t it1 = it0 + FLUSH_IT < niter ? it0 + FLUSH_IT : niter;
             if (lane == 0) {
@@ -472,10 +476,16 @@ linear_train_tc_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __res
                 // products still to issue in this window (only the very last iteration can be ragged)
                 uint32_t remaining = (it1 - it0) * T3_NPROD - (it1 == niter ? uint32_t(T3_NPROD - nlast) : 0u);
                 while (remaining) {
-                    uint32_t cur[4];
+                    uint32_t cur[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
                     asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
                                  : "=r"(cur[0]), "=r"(cur[1]), "=r"(cur[2]), "=r"(cur[3]) : "r"(status_addr) : "memory");
-                    if (((cur[0] ^ seen[0]) | (cur[1] ^ seen[1]) | (cur[2] ^ seen[2]) | (cur[3] ^ seen[3])) == 0u) {
+                    if (NSW > 4)
+                        asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                     : "=r"(cur[4]), "=r"(cur[5]), "=r"(cur[6]), "=r"(cur[7]) : "r"(status_addr + 16) : "memory");
+                    uint32_t diff = 0;
+#pragma unroll
+                    for (int i = 0; i < NSW; ++i) diff |= cur[i] ^ seen[i];
+                    if (diff == 0u) {
                         __nanosleep(64);
                         continue;
                     }
@@ -494,7 +504,7 @@ linear_train_tc_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __res
                         }
                     }
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) seen[i] = cur[i];
+                    for (int i = 0; i < NSW; ++i) seen[i] = cur[i];
                 }
                 umma_commit(bar_done);
                 mbar_wait(bar_done, flushes & 1u);
