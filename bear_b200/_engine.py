@@ -165,6 +165,20 @@ class Optimizer:
             self.v.addcmul_(grads, grads)
             params.sub_(self.lr * grads / (self.v.sqrt() + 1e-7))
 
+    def step_and_clear(self, fp, loss_slot, loss_scale):
+        """One optimizer step on the (already allreduced) flat buffer ``fp.grad`` = [loss, grads...]: records
+        ``loss_scale * loss`` into ``loss_slot`` (a one-element device view, or None), updates ``fp.flat`` and
+        clears ``fp.grad`` for the next accumulation.  Adam: one kernel launch (bear_adam_step)."""
+        if self.name == 'Adam':
+            check(lib.bear_adam_step(ptr(fp.flat), ptr(fp.grad), ptr(self.m), ptr(self.v), fp.total, self.lr, 0.9, 0.999,
+                                     1e-7, ptr(self.step), ptr(loss_slot) if loss_slot is not None else None,
+                                     float(loss_scale), 1, _lib.stream()))
+            return
+        if loss_slot is not None:
+            loss_slot.copy_(loss_scale * fp.grad[:1])
+        self.apply(fp.flat, fp.grad[1:])
+        fp.grad.zero_()
+
 
 def workspace(table, nparams=0):
     return torch.empty(lib.bear_workspace_doubles(table.num_rows, table.lag, nparams), dtype=torch.float64,
@@ -203,41 +217,48 @@ def train_loop(data, num_kmers, ds_loc, train_ar, acc_steps, fp, optimizer_name,
                writer=None, loss_save=None, graph_safe=False):
     """The loop of bear_net.train (bear_net.py:293-315): ``step_fn(r0, n, scale)`` adds the loss and
     gradients of one batch into ``fp.grad``; every ``acc_steps`` batches the buffer is allreduced,
-    the loss recorded and the optimizer applied.
-
-    Small tables make this loop launch-bound (the reference's tutorial: 10 000 steps over 1 365 rows), so when
-    the step only launches libbear_b200 kernels (``graph_safe``) one epoch is captured in a CUDA graph
-    after an eager first epoch and replayed for the remaining ones (capture costs ~0.2 s, so only runs of
-    >= BEAR_GRAPH_MIN_EPOCHS = 2048 epochs use it)."""
+    the loss recorded and the optimizer applied (one launch)."""
     opt = Optimizer(optimizer_name, learning_rate, fp.total, fp.flat.device)
     fp.grad.zero_()
     record = writer is not None or loss_save is not None
     nb, reps = len(data.ranges), data.repeats
-    steps_done, losses = 0, []          # losses: (first step index, tensor of -loss/acc_steps per update)
+    upd = nb // acc_steps                 # optimizer steps per epoch when nb is a multiple of acc_steps
+    dev = fp.flat.device
 
-    def one_epoch(loss_buf):
+    def one_epoch(loss_buf, first_step=0, slot0=0):
+        """Every batch of one pass over the data; per optimizer step (every ``acc_steps`` batches, counted over the whole
+        run as in bear_net.py:300): the batch kernels, ONE allreduce of the flat buffer, ONE optimizer launch (loss
+        record + update + clearing of the buffer).  Returns the number of optimizer steps taken."""
+        u = 0
         for i, ((r0, n), gB) in enumerate(zip(data.ranges, data.global_rows)):
             step_fn(r0, n, float(num_kmers) / float(gB))
-            if (i + 1) % acc_steps == 0:
+            if (first_step + i + 1) % acc_steps == 0:
                 allreduce_sum(fp.grad)
-                if loss_buf is not None:
-                    loss_buf[(i + 1) // acc_steps - 1].copy_(-fp.grad[0] / acc_steps)
-                opt.apply(fp.flat, fp.grad[1:])
-                fp.grad.zero_()
+                opt.step_and_clear(fp, loss_buf[slot0 + u:slot0 + u + 1] if loss_buf is not None else None, -1.0 / acc_steps)
+                u += 1
+        return u
 
-    min_epochs = int(os.environ.get('BEAR_GRAPH_MIN_EPOCHS', 2048))       # capture costs ~0.2 s, replay saves ~80 us / epoch
-    use_graph = (graph_safe and fp.flat.is_cuda and world()[1] == 1 and reps >= min_epochs and 0 < nb <= 64
-                 and nb % acc_steps == 0 and not os.environ.get('BEAR_NO_GRAPH'))
+    # Small batches make this loop launch-bound (the reference's tutorial: 10 000 steps over 1 365 rows; a 2^22-row
+    # global batch on 8 GPUs is 27 us of kernel time per step), so when the step only launches libbear_b200 kernels
+    # (``graph_safe``) one epoch -- batch kernels, NCCL allreduce and optimizer launch of every step -- is captured in a
+    # CUDA graph after an eager first epoch and replayed for the remaining ones.  Capture costs ~0.2 s, so only runs
+    # that replay >= BEAR_GRAPH_MIN_LAUNCHES launches use it.
+    min_launches = int(os.environ.get('BEAR_GRAPH_MIN_LAUNCHES', 8192))
+    use_graph = (graph_safe and fp.flat.is_cuda and reps >= 2 and 0 < nb <= 4096 and nb % acc_steps == 0
+                 and (reps - 1) * nb * 4 >= min_launches and not os.environ.get('BEAR_NO_GRAPH'))
+    if world()[1] > 1 and os.environ.get('BEAR_NO_NCCL_GRAPH'):
+        use_graph = False
+    losses = []
     if use_graph:
-        upd = nb // acc_steps
-        loss_buf = torch.zeros(upd, dtype=torch.float64, device=fp.flat.device)
+        loss_buf = torch.zeros(max(upd, 1), dtype=torch.float64, device=dev)
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)
         with torch.cuda.stream(side):           # eager first epoch (also warms up everything capture needs)
             one_epoch(loss_buf)
         cur.wait_stream(side)
-        losses.append(loss_buf.clone())
+        if record:
+            losses.append(loss_buf.clone())
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             one_epoch(loss_buf)
@@ -245,27 +266,21 @@ def train_loop(data, num_kmers, ds_loc, train_ar, acc_steps, fp, optimizer_name,
             graph.replay()
             if record:
                 losses.append(loss_buf.clone())
-        flat_losses = torch.cat(losses) if record else None
         update_steps = [(e * nb) + (u + 1) * acc_steps for e in range(reps) for u in range(upd)]
     else:
-        vals, update_steps, step = [], [], 1
-        for r0, n, gB in data.batches():
-            step_fn(r0, n, float(num_kmers) / float(gB))
-            if step % acc_steps == 0:
-                allreduce_sum(fp.grad)
-                if record:
-                    vals.append((-fp.grad[0] / acc_steps).clone())
-                    update_steps.append(step)
-                opt.apply(fp.flat, fp.grad[1:])
-                fp.grad.zero_()
-            step += 1
-        flat_losses = torch.stack(vals) if vals else None
-    if record and flat_losses is not None:
-        for s, v in zip(update_steps, flat_losses.cpu().tolist()):     # one D2H copy at the end
+        total_upd = (reps * nb) // acc_steps
+        all_losses = torch.zeros(max(total_upd, 1), dtype=torch.float64, device=dev) if record else None
+        done = 0
+        for e in range(reps):
+            done += one_epoch(all_losses, e * nb, done)
+        losses = [all_losses[:done]] if record else []
+        update_steps = [(u + 1) * acc_steps for u in range(done)]
+    if record and update_steps:
+        for s_, v_ in zip(update_steps, torch.cat(losses).cpu().tolist()):     # one D2H copy at the end
             if loss_save is not None:
-                loss_save.append(v)
+                loss_save.append(v_)
             if writer is not None and hasattr(writer, 'add_scalar'):
-                writer.add_scalar('elbo', v, s)
+                writer.add_scalar('elbo', v_, s_)
 
 
 def explicit_f(ar_func, table, r0, n, extra=None):
@@ -327,10 +342,10 @@ def eval_loop(data, ds_loc_train, ds_loc_test, h, van_reg, head, head_ptr_fn, se
         vp = van[p * M:(p + 1) * M].to(dev)
         Hp, Vp = hp.numel(), vp.numel()
         acc = torch.zeros(2 * Hp + 2 * Vp + 3, dtype=torch.float64, device=dev)
-        for r0, n, _ in data.batches():
+        for (r0, n), gid in list(zip(data.ranges, data.row_ids)) * data.repeats:
             keep, hptr = head_ptr_fn(r0, n)
             check(lib.bear_eval_step(ptr(k), test_ptr, train_ptr, table.stride, r0, n, table.lag, head, hptr,
-                                     ptr(hp) if Hp else None, Hp, ptr(vp) if Vp else None, Vp, seed, ptr(acc),
+                                     ptr(hp) if Hp else None, Hp, ptr(vp) if Vp else None, Vp, seed, gid, ptr(acc),
                                      ptr(ws), _lib.stream()))
             del keep
         acc = allreduce_sum(acc).cpu()

@@ -71,13 +71,14 @@ _SIGNATURES = {
     'bear_workspace_doubles': (_i64, [_i64, _i32, _i32]),
     'bear_linear_train_step': (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _vp, _vp, _f64, _i32, _vp, _vp, _vp, _vp]),
     'bear_dm_train_step_explicit': (_i32, [_vp, _i64, _i64, _i64, _vp, _vp, _f64, _i32, _vp, _vp, _vp, _vp, _vp]),
-    'bear_eval_step': (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _i32, _vp, _i32, _i64, _vp, _vp, _vp]),
+    'bear_eval_step': (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _i32, _vp, _i32, _i64, _i64, _vp, _vp, _vp]),
     'bear_bmm_likelihood': (_i32, [_vp, _i64, _i64, _i64, _i32, _i32, _vp, _i32, _vp, _vp, _vp]),
     'bear_loggamma_sample': (_i32, [_vp, _i64, _i64, _i64, _vp, _vp]),
     'bear_log_normalize': (_i32, [_vp, _i64, _i32, _vp]),
     'bear_synth_table': (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _i32, _i64, _i32, _i32, _vp]),
     'bear_count_transitions': (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _i64, _vp, _vp]),
     'bear_gather_table': (_i32, [_vp, _vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp]),
+    'bear_adam_step': (_i32, [_vp, _vp, _vp, _vp, _i64, _f64, _f64, _f64, _f64, _vp, _vp, _f64, _i32, _vp]),
     'bear_adam_update': (_i32, [_vp, _vp, _vp, _vp, _i64, _f64, _f64, _f64, _f64, _vp, _vp]),
     'bear_cnn_supported': (_i32, [_i32, _i32, _i32, _i32]),
     'bear_cnn_num_params': (_i64, [_i32, _i32, _i32, _i32]),

@@ -623,7 +623,7 @@ extern "C" int bear_dm_train_step_explicit(const uint32_t* d_col, int64_t stride
 
 extern "C" int bear_eval_step(const uint64_t* d_kmers, const uint32_t* d_test_col, const uint32_t* d_train_col,
                               int64_t stride, int64_t row0, int64_t n, int lag, int head, const double* d_head,
-                              const double* d_h, int H, const double* d_van, int V, int64_t seed,
+                              const double* d_h, int H, const double* d_van, int V, int64_t seed, int64_t row_id0,
                               double* d_acc, double* d_workspace, void* stream) {
     const char* fn = "bear_eval_step";
     BEAR_REQUIRE(d_test_col && d_acc && d_workspace, fn);
@@ -644,10 +644,10 @@ extern "C" int bear_eval_step(const uint64_t* d_kmers, const uint32_t* d_test_co
     const bool ht = tr != nullptr;
     int rc;
     switch (head) {
-        case BEAR_HEAD_LINEAR: rc = launch_eval_nm<BEAR_HEAD_LINEAR>(small, ht, grid, smem, st, km, te, tr, stride, row0, n, lag, d_head, d_h, H, d_van, V, seed, d_workspace); break;
-        case BEAR_HEAD_EXPLICIT: rc = launch_eval_nm<BEAR_HEAD_EXPLICIT>(small, ht, grid, smem, st, km, te, tr, stride, row0, n, lag, d_head, d_h, H, d_van, V, seed, d_workspace); break;
-        case BEAR_HEAD_STOP: rc = launch_eval_nm<BEAR_HEAD_STOP>(small, ht, grid, smem, st, km, te, tr, stride, row0, n, lag, d_head, d_h, H, d_van, V, seed, d_workspace); break;
-        default: rc = launch_eval_nm<BEAR_HEAD_NONE>(small, ht, grid, smem, st, km, te, tr, stride, row0, n, lag, d_head, d_h, H, d_van, V, seed, d_workspace); break;
+        case BEAR_HEAD_LINEAR: rc = launch_eval_nm<BEAR_HEAD_LINEAR>(small, ht, grid, smem, st, km, te, tr, stride, row_id0, n, lag, d_head, d_h, H, d_van, V, seed, d_workspace); break;
+        case BEAR_HEAD_EXPLICIT: rc = launch_eval_nm<BEAR_HEAD_EXPLICIT>(small, ht, grid, smem, st, km, te, tr, stride, row_id0, n, lag, d_head, d_h, H, d_van, V, seed, d_workspace); break;
+        case BEAR_HEAD_STOP: rc = launch_eval_nm<BEAR_HEAD_STOP>(small, ht, grid, smem, st, km, te, tr, stride, row_id0, n, lag, d_head, d_h, H, d_van, V, seed, d_workspace); break;
+        default: rc = launch_eval_nm<BEAR_HEAD_NONE>(small, ht, grid, smem, st, km, te, tr, stride, row_id0, n, lag, d_head, d_h, H, d_van, V, seed, d_workspace); break;
     }
     if (rc) return rc;
     BEAR_LAUNCH_CHECK("eval_kernel");

@@ -116,6 +116,32 @@ __global__ void adam_kernel(double* __restrict__ p, const double* __restrict__ g
 
 __global__ void bump_kernel(int64_t* step) { step[0] += 1; }
 
+// One optimizer step of the training loop as ONE launch (small parameter vectors: one CTA): records the loss,
+// applies Adam, clears the accumulated gradient buffer and advances the step counter.
+__global__ void __launch_bounds__(1024)
+adam_step_kernel(double* __restrict__ p, double* __restrict__ flat, double* __restrict__ m, double* __restrict__ v, int64_t n,
+                 double lr, double b1, double b2, double eps, int64_t* __restrict__ step, double* __restrict__ loss_out,
+                 double loss_scale, int zero_flat) {
+    const double t = double(step[0] + 1);
+    const double lr_t = lr * sqrt(1.0 - pow(b2, t)) / (1.0 - pow(b1, t));
+    const double loss = flat[0];
+    __syncthreads();                                     // every thread has read the step counter and the loss
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const double gi = flat[1 + i];
+        const double mi = b1 * m[i] + (1.0 - b1) * gi;
+        const double vi = b2 * v[i] + (1.0 - b2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        p[i] -= lr_t * mi / (sqrt(vi) + eps);
+        if (zero_flat) flat[1 + i] = 0.0;
+    }
+    if (threadIdx.x == 0) {
+        if (loss_out) loss_out[0] = loss_scale * loss;
+        if (zero_flat) flat[0] = 0.0;
+        step[0] += 1;
+    }
+}
+
 }  // namespace
 
 #define ST(stream) static_cast<cudaStream_t>(stream)
@@ -144,6 +170,18 @@ extern "C" int bear_ref_head_bwd(const uint32_t* d_ref_col, int64_t stride, int6
     BEAR_LAUNCH_CHECK("ref_head_bwd_kernel");
     sum2_kernel<<<1, 32, 0, ST(stream)>>>(d_workspace, grid, d_flat2);
     BEAR_LAUNCH_CHECK("sum2_kernel");
+    return BEAR_OK;
+}
+
+extern "C" int bear_adam_step(double* d_params, double* d_flat, double* d_m, double* d_v, int64_t n, double lr, double beta1,
+                              double beta2, double eps, int64_t* d_step, double* d_loss_out, double loss_scale, int zero_flat,
+                              void* stream) {
+    const char* fn = "bear_adam_step";
+    BEAR_REQUIRE(n >= 0 && n <= (int64_t(1) << 22), fn);
+    BEAR_REQUIRE(d_params && d_flat && d_m && d_v && d_step, fn);
+    adam_step_kernel<<<1, 1024, 0, ST(stream)>>>(d_params, d_flat, d_m, d_v, n, lr, beta1, beta2, eps, d_step, d_loss_out, loss_scale,
+                                                 zero_flat);
+    BEAR_LAUNCH_CHECK("adam_step_kernel");
     return BEAR_OK;
 }
 

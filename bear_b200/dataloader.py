@@ -263,7 +263,7 @@ class KmerDataset:
     reference's ``num_kmers / batch`` factor (bear_net.py:190) independent of the GPU count.
     """
 
-    def __init__(self, table, batch_size, repeats=1, ranges=None, global_rows=None, map_fn=None):
+    def __init__(self, table, batch_size, repeats=1, ranges=None, global_rows=None, map_fn=None, row_ids=None):
         self.table = table
         self.batch_size = int(batch_size)
         self.repeats = int(repeats)
@@ -273,11 +273,15 @@ class KmerDataset:
             global_rows = [n for _, n in ranges]
         self.ranges = ranges                  # local (row0, n) per batch
         self.global_rows = global_rows        # rows of the same batch summed over all ranks
+        # index, in the whole (unsharded) table, of the first local row of every batch: keys the argmax tie-break
+        # noise of the evaluation, so that results do not depend on the number of ranks
+        self.row_ids = [r0 for r0, _ in ranges] if row_ids is None else row_ids
         self.map_fn = map_fn
 
     # tf.data-like surface used by the reference scripts
     def repeat(self, count):
-        return KmerDataset(self.table, self.batch_size, self.repeats * int(count), self.ranges, self.global_rows, self.map_fn)
+        return KmerDataset(self.table, self.batch_size, self.repeats * int(count), self.ranges, self.global_rows, self.map_fn,
+                           self.row_ids)
 
     def cache(self):
         return self
@@ -288,7 +292,7 @@ class KmerDataset:
     def map(self, fn, num_parallel_calls=None):
         prev = self.map_fn
         f = fn if prev is None else (lambda *a: fn(*_as_tuple(prev(*a))))
-        return KmerDataset(self.table, self.batch_size, self.repeats, self.ranges, self.global_rows, f)
+        return KmerDataset(self.table, self.batch_size, self.repeats, self.ranges, self.global_rows, f, self.row_ids)
 
     def __len__(self):
         return len(self.ranges) * self.repeats
@@ -305,16 +309,17 @@ class KmerDataset:
             return self
         if self.table.kmers_host is None:
             raise ValueError('shard() needs a host table; device-generated tables are built per rank')
-        idx, ranges, grows, o = [], [], [], 0
-        for r0, n in self.ranges:
+        idx, ranges, grows, ids, o = [], [], [], [], 0
+        for (r0, n), gid in zip(self.ranges, self.row_ids):
             per = -(-n // world)
             lo, hi = min(rank * per, n), min((rank + 1) * per, n)
             idx.append(np.arange(r0 + lo, r0 + hi))
             ranges.append((o, hi - lo))
             grows.append(n)
+            ids.append(gid + lo)
             o += hi - lo
         local = self.table.take(np.concatenate(idx) if idx else np.zeros(0, np.int64))
-        return KmerDataset(local, self.batch_size, self.repeats, ranges, grows, self.map_fn)
+        return KmerDataset(local, self.batch_size, self.repeats, ranges, grows, self.map_fn, ids)
 
     def __iter__(self):
         """Yields the reference's batch elements: (KmerBatch, counts float64 [B, G, A1] on the device),

@@ -190,13 +190,14 @@ int bear_dm_train_step_explicit(const uint32_t* d_col, int64_t stride, int64_t r
  * head = BEAR_HEAD_LINEAR (d_head = mat), BEAR_HEAD_EXPLICIT (d_head = f[n, A1], row i = table row row0 + i),
  * BEAR_HEAD_STOP or BEAR_HEAD_NONE (f = 0: ear degenerates to conc = train + eps).
  * Argmax tie-breaking noise: sigma = 100*eps (ear, van) / eps (arm) as in core.py:70,135; seed < 0
- * disables the noise. */
+ * disables the noise.  The noise of a row is a pure function of (seed, row_id0 + i, model), where row_id0 is the
+ * index of row `row0` in the whole (unsharded) table: results do not depend on how rows are spread over GPUs. */
 #define BEAR_MAX_MODELS 8
 int bear_eval_step(const uint64_t* d_kmers, const uint32_t* d_test_col, const uint32_t* d_train_col,
                    int64_t stride, int64_t row0, int64_t n, int lag,
                    int head, const double* d_head,
                    const double* d_h /* [H] */, int H, const double* d_van /* [V] */, int V,
-                   int64_t seed, double* d_acc, double* d_workspace, void* stream);
+                   int64_t seed, int64_t row_id0, double* d_acc, double* d_workspace, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Device: the CNN autoregressive head (ar_funcs.make_ar_func_cnn, ar_funcs.py:49-99) fused with the
@@ -261,6 +262,15 @@ int bear_ref_head_bwd(const uint32_t* d_ref_col, int64_t stride, int64_t row0, i
  * The step counter lives on the device so the update is CUDA-graph capturable. */
 int bear_adam_update(double* d_params, const double* d_grads, double* d_m, double* d_v, int64_t n, double lr,
                      double beta1, double beta2, double eps, int64_t* d_step, void* stream);
+
+/* One optimizer step of bear_net.train's loop (bear_net.py:300-313) in a single launch, for the flat buffers of the
+ * training entry points: d_flat = [loss, d h_signed, d params...] (1 + n doubles, after the allreduce); the Adam update
+ * of bear_adam_update is applied to d_params[n] with d_flat[1..n]; if d_loss_out is not NULL it receives
+ * loss_scale * d_flat[0] (the recorded "elbo" is -loss / acc_steps); with zero_flat != 0 d_flat is cleared for the next
+ * accumulation; ++*d_step.  n <= 2^22. */
+int bear_adam_step(double* d_params, double* d_flat, double* d_m, double* d_v, int64_t n, double lr, double beta1,
+                   double beta2, double eps, int64_t* d_step, double* d_loss_out, double loss_scale, int zero_flat,
+                   void* stream);
 
 /* Deterministic synthetic packed table for benchmarks and large-scale parity checks: rows
  * [row_begin, row_begin+n) of the table defined by (seed, lag, G, regime) -- see DESIGN.md.

@@ -68,6 +68,16 @@ def one_hot(kmers, alphabet='dna', dtype=torch.float64):
     return out
 
 
+def one_hot_bytes(kmers, alphabet='dna', dtype=torch.float64):
+    """core.py:156-174 on a numpy array of equal-length byte strings (dtype 'S<lag>'), vectorised the way the TF
+    graph is: bytes_split -> equal against the alphabet (broadcast) -> cast.  Same values as ``one_hot``."""
+    kmers = np.asarray(kmers)
+    lag = kmers.dtype.itemsize
+    sym = kmers.view(np.uint8).reshape(len(kmers), lag)
+    alph = np.frombuffer(''.join(ALPHABETS_IN[alphabet]).encode(), dtype=np.uint8)
+    return torch.from_numpy(sym[:, :, None] == alph[None, None, :]).to(dtype)
+
+
 def read_tsv(path, num_ds, alphabet='dna', header=False):
     """dataloader.py:6-50 dense TSV ``kmer \\t [[g0...],[g1...],...]``.
     Returns (list of kmer str, float64 ndarray [K, num_ds, A+1])."""

@@ -315,7 +315,7 @@ def test_linear_head_exact_fallback_on_extreme_logits(cuda):
     h = torch.tensor([1.5], dtype=torch.float64, device=cuda)
     van = torch.tensor([1.0], dtype=torch.float64, device=cuda)
     check(lib.bear_eval_step(ptr(k), table.col_ptr(0), None, table.stride, 0, K, lag, _lib.HEAD_LINEAR, ptr(mat_d), ptr(h), 1,
-                             ptr(van), 1, -1, ptr(acc), ptr(ws), _lib.stream()))
+                             ptr(van), 1, -1, 0, ptr(acc), ptr(ws), _lib.stream()))
     want = _oracle_eval(codes, counts, lag, 0, -1, [1.5], [1.0], mat)
     assert abs(float(acc[0]) - float(want[0][0])) <= 1e-9 * abs(float(want[0][0]))
     assert abs(float(acc[1]) - float(want[1])) <= 1e-9 * abs(float(want[1]))

@@ -199,3 +199,11 @@ def test_cancelling_term_is_rounding_noise(ysd1):
     a = O.dm_counts_log_prob(c.sum(-1), conc, c, True).numpy()
     b = O.dm_counts_log_prob(c.sum(-1), conc, c, False).numpy()
     assert np.max(np.abs(a - b) / np.abs(b)) < 1e-13
+
+
+def test_vectorised_one_hot_matches_the_per_character_restatement():
+    """bench.py's CPU arm builds the one-hot input from byte strings every step (as the reference's tf.data map does,
+    bear_net.py:268-273) with the vectorised form of core.tf_one_hot; it must equal the per-character restatement."""
+    rng = np.random.default_rng(0)
+    kmers = np.array([''.join(rng.choice(list('ACGT['), size=7)).encode() for _ in range(200)] + [b'ACGTNNN'], dtype='S7')
+    assert torch.equal(O.one_hot_bytes(kmers), O.one_hot(list(kmers)))

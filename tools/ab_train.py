@@ -42,7 +42,7 @@ for lag, regime, name in ((20, 0, 'lag20'), (20, 2, 'lag20-sorted'), (13, 0, 'la
 
     def evalk():
         check(lib.bear_eval_step(ptr(kmers), ptr(counts), None, stride, 0, n, lag, _lib.HEAD_LINEAR, ptr(mat), ptr(h), 1,
-                                 ptr(alpha), 3, 7, ptr(eacc), ptr(ws), _lib.stream()))
+                                 ptr(alpha), 3, 7, 0, ptr(eacc), ptr(ws), _lib.stream()))
     fns = [(train, 'train'), (evalk, 'eval')]
     if legacy is not None:
         flat.zero_()

@@ -107,12 +107,12 @@ def main():
         h = torch.ones(1, dtype=torch.float64, device=dev)
         eacc = torch.zeros(11, dtype=torch.float64, device=dev)
         t = timed(lambda: check(lib.bear_eval_step(ptr(kmers), ptr(counts), None, stride, 0, n, lag, _lib.HEAD_LINEAR, ptr(mat), ptr(h), 1,
-                                                   ptr(alpha), 3, 7, ptr(eacc), ptr(ws), _lib.stream())))
+                                                   ptr(alpha), 3, 7, 0, ptr(eacc), ptr(ws), _lib.stream())))
         report('eval_kernel<LINEAR> H=1 V=3 no-train [%s]' % tag, t, n, 28)
         if G > 1:
             tr = ctypes_off(counts, 5 * stride * 4)
             t = timed(lambda: check(lib.bear_eval_step(ptr(kmers), tr, ptr(counts), stride, 0, n, lag, _lib.HEAD_LINEAR, ptr(mat), ptr(h), 1,
-                                                       ptr(alpha), 3, 7, ptr(eacc), ptr(ws), _lib.stream())))
+                                                       ptr(alpha), 3, 7, 0, ptr(eacc), ptr(ws), _lib.stream())))
             report('eval_kernel<LINEAR> H=1 V=3 heldout [%s]' % tag, t, n, 48)
         m = min(n, 1 << 24)
         f = torch.full((m, 5), 0.2, dtype=torch.float64, device=dev)

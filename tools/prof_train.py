@@ -29,7 +29,7 @@ for _ in range(2):
     check(lib.bear_linear_train_step(ptr(kmers), ptr(counts), stride, 0, n, lag, ptr(mat), ptr(hs), 1.0, 0, ptr(flat), None,
                                      ptr(ws), _lib.stream()))
     check(lib.bear_eval_step(ptr(kmers), ptr(counts), None, stride, 0, n, lag, _lib.HEAD_LINEAR, ptr(mat), ptr(h), 1,
-                             ptr(alpha), 3, 7, ptr(eacc), ptr(ws), _lib.stream()))
+                             ptr(alpha), 3, 7, 0, ptr(eacc), ptr(ws), _lib.stream()))
 torch.cuda.synchronize()
 print('ok', float(flat[0]))
 if os.environ.get('BMM'):
