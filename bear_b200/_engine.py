@@ -316,10 +316,11 @@ def explicit_train_step(table, ds_loc, r0, n, scale, train_ar, fp, ws, f_fn):
 # ---------------------------------------------------------------------------------------------
 # evaluation
 # ---------------------------------------------------------------------------------------------
-def eval_loop(data, ds_loc_train, ds_loc_test, h, van_reg, head, head_ptr_fn, seed):
+def eval_loop(data, ds_loc_train, ds_loc_test, h, van_reg, head, head_ptr_fn, seed, ref=None):
     """bear_net.evaluation's accumulation (bear_net.py:439-457) on the packed table.  ``head`` is a
     BEAR_HEAD_* id; ``head_ptr_fn(r0, n)`` returns (tensor kept alive, explicit row offset) for the
-    head argument of bear_eval_step.  Returns float64 CPU tensors
+    head argument of bear_eval_step.  ``ref`` = (ds_loc_ref, net id, mat or None, tau_signed, net_weight_signed) routes
+    the pass through the fused reference-head kernel bear_ref_eval_step instead.  Returns float64 CPU tensors
     (ll_ear[H], ll_arm, ll_van[V], cor_ear[H], cor_arm, cor_van[V], total_len)."""
     table = data.table
     k, c = table.device_tensors()
@@ -343,6 +344,13 @@ def eval_loop(data, ds_loc_train, ds_loc_test, h, van_reg, head, head_ptr_fn, se
         Hp, Vp = hp.numel(), vp.numel()
         acc = torch.zeros(2 * Hp + 2 * Vp + 3, dtype=torch.float64, device=dev)
         for (r0, n), gid in list(zip(data.ranges, data.row_ids)) * data.repeats:
+            if ref is not None:
+                ds_loc_ref, net, mat, tau_signed, nw_signed = ref
+                check(lib.bear_ref_eval_step(ptr(k), test_ptr, train_ptr, table.col_ptr(ds_loc_ref), table.stride, r0, n,
+                                             table.lag, net, ptr(mat), ptr(tau_signed), ptr(nw_signed),
+                                             ptr(hp) if Hp else None, Hp, ptr(vp) if Vp else None, Vp, seed, gid, ptr(acc),
+                                             ptr(ws), _lib.stream()))
+                continue
             keep, hptr = head_ptr_fn(r0, n)
             check(lib.bear_eval_step(ptr(k), test_ptr, train_ptr, table.stride, r0, n, table.lag, head, hptr,
                                      ptr(hp) if Hp else None, Hp, ptr(vp) if Vp else None, Vp, seed, gid, ptr(acc),

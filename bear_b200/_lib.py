@@ -80,6 +80,9 @@ _SIGNATURES = {
     'bear_gather_table': (_i32, [_vp, _vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp]),
     'bear_adam_step': (_i32, [_vp, _vp, _vp, _vp, _i64, _f64, _f64, _f64, _f64, _vp, _vp, _f64, _i32, _vp]),
     'bear_adam_update': (_i32, [_vp, _vp, _vp, _vp, _i64, _f64, _f64, _f64, _f64, _vp, _vp]),
+    'bear_ref_train_step': (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _f64, _i32, _vp, _vp, _vp, _vp]),
+    'bear_ref_eval_step': (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _i64, _i64, _vp,
+                                  _vp, _vp]),
     'bear_cnn_supported': (_i32, [_i32, _i32, _i32, _i32]),
     'bear_cnn_num_params': (_i64, [_i32, _i32, _i32, _i32]),
     'bear_cnn_head_forward': (_i32, [_vp, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),

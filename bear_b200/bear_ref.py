@@ -6,9 +6,11 @@ Mirrors the reference's ``bear_model/bear_ref.py`` (``_counts_to_probs`` bear_re
 ``change_scope_params`` :136-204, ``train`` :262-389, ``evaluation`` :453-539) with the same argument
 names and order; params = [h_signed, tau_signed, net_weight_signed, *net params].
 
-Device path per batch: embedded net g(k) (NULL for the stop head; torch ops for nets) ->
-``bear_ref_head`` (Jukes-Cantor + mixing from the packed reference column) ->
-``bear_dm_train_step_explicit`` (fused DM forward/backward) -> ``bear_ref_head_bwd`` (d tau, d net
+Device path: with the stop net (the reference's bear_stop_*.cfg) one fused kernel per training batch
+(``bear_ref_train_step``) and one per evaluation batch (``bear_ref_eval_step``, also for the linear net): the
+Jukes-Cantor head lives in registers, no f array exists in memory.  Other nets, per training batch: embedded net
+g(k) (torch ops / the fused CNN kernels) -> ``bear_ref_head`` (Jukes-Cantor + mixing from the packed reference
+column) -> ``bear_dm_train_step_explicit`` (fused DM forward/backward) -> ``bear_ref_head_bwd`` (d tau, d net
 weight, d g) -> the net's backward.
 
 Deviation from the reference, on purpose: ``bear_ref._evaluation_step`` reads
@@ -136,7 +138,16 @@ def train(data, num_kmers, epochs, ds_loc, ds_loc_ref, alphabet, lag, make_ar_fu
     for p in params[3:]:
         p.requires_grad_(True)
 
+    stop_net = table.A1 == 5 and eng.head_kind(ar_func.net_func) == 'stop'
+
     def step_fn(r0, n, scale):
+        if stop_net:
+            # stop net (bear_stop_bear.cfg / bear_stop_ar.cfg): head, loss and the gradients of [h, tau, net weight] in ONE
+            # kernel over the data and reference columns; fp.grad = [loss, d h, d tau_signed, d net_weight_signed]
+            check(lib.bear_ref_train_step(table.col_ptr(ds_loc), table.col_ptr(ds_loc_ref), table.stride, r0, n, ptr(h_signed),
+                                          ptr(ar_func.tau_signed), ptr(ar_func.net_weight_signed), scale, int(train_ar),
+                                          ptr(fp.grad), None, ptr(ws), _lib.stream()))
+            return
         for c0 in range(r0, r0 + n, eng.EXPLICIT_CHUNK):
             cn = min(eng.EXPLICIT_CHUNK, r0 + n - c0)
             with torch.enable_grad():
@@ -159,7 +170,7 @@ def train(data, num_kmers, epochs, ds_loc, ds_loc_ref, alphabet, lag, make_ar_fu
                 t.grad = None
 
     eng.train_loop(data, num_kmers, ds_loc, train_ar, acc_steps, fp, optimizer_name, learning_rate, step_fn,
-                   writer=writer, loss_save=loss_save)
+                   writer=writer, loss_save=loss_save, graph_safe=stop_net)
     for p in params:
         p.requires_grad_(False)
     return params, h_signed, ar_func
@@ -175,6 +186,15 @@ def evaluation(data, ds_loc_train, ds_loc_test, ds_loc_ref, alphabet, h, ar_func
         return _ref_f(ar_func, table, ds_loc_ref, c0, cn, _net_values(ar_func, table, c0, cn))[0]
 
     hv = float(h.item() if hasattr(h, 'item') else h)
+    # stop and linear nets on DNA / RNA tables: ONE fused kernel per batch (bear_ref_eval_step: Jukes-Cantor head in
+    # registers); other nets: f is materialised by torch ops / the CNN kernel and read back by bear_eval_step
+    ref = None
+    kind = eng.head_kind(ar_func.net_func)
+    if table.A1 == 5 and kind == 'stop':
+        ref = (ds_loc_ref, _lib.HEAD_STOP, None, ar_func.tau_signed, ar_func.net_weight_signed)
+    elif eng.fused_linear_ok(ar_func.net_func, table):
+        ref = (ds_loc_ref, _lib.HEAD_LINEAR, ar_func.net_func.params[0].detach().contiguous(), ar_func.tau_signed,
+               ar_func.net_weight_signed)
     ll_ear, ll_arm, ll_van, ce, ca, cv, tot = eng.eval_loop(data, ds_loc_train, ds_loc_test, [hv], van_reg,
-                                                            _lib.HEAD_EXPLICIT, eng.explicit_head_ptr_fn(f_fn), seed)
+                                                            _lib.HEAD_EXPLICIT, eng.explicit_head_ptr_fn(f_fn), seed, ref=ref)
     return eng.finish_evaluation(ll_ear[0], ll_arm, ll_van, ce[0], ca, cv, tot)

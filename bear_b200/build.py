@@ -22,9 +22,9 @@ CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libbear_b200.so')
 OBJ = os.path.join(HERE, '_build')
 
-SOURCES = ['bear_pack.cpp', 'bear_dense.cu', 'bear_fused.cu', 'bear_train.cu', 'bear_heads.cu', 'bear_count.cu',
-           'bear_cnn.cu']
-HEADERS = ['bear_common.cuh', 'bear_dm_row.cuh', 'bear_host.h', 'bear_linear_head.cuh', 'bear_sm100.cuh']
+SOURCES = ['bear_pack.cpp', 'bear_dense.cu', 'bear_fused.cu', 'bear_eval_misc.cu', 'bear_eval_lin.cu', 'bear_eval_ref.cu',
+           'bear_train.cu', 'bear_heads.cu', 'bear_count.cu', 'bear_cnn.cu']
+HEADERS = ['bear_common.cuh', 'bear_dm_row.cuh', 'bear_host.h', 'bear_linear_head.cuh', 'bear_sm100.cuh', 'bear_eval.cuh']
 
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a',

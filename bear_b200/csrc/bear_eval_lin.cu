@@ -1,0 +1,10 @@
+// eval_tile_kernel (bear_eval.cuh) instantiated for the head variants BEAR_HEAD_LINEAR.
+#define BEAR_EVAL_IMPL
+#include "bear_eval.cuh"
+
+int bear_eval::launch_linear(const EvalArgs& a) {
+    switch (a.head) {
+        case BEAR_HEAD_LINEAR: return launch_head<BEAR_HEAD_LINEAR>(a);
+    }
+    return BEAR_ERR_ARG;
+}

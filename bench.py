@@ -730,47 +730,48 @@ def leg_configs(c, args):
         barrier(c)
         return max_over_ranks(c, e0.elapsed_time(e1) * 1e-3 / reps)
 
-    # ---- C1: bundled ysd1 lag-5 table, end to end from the TSV (parse -> upload -> 10 000 Adam steps -> evaluation) ----
-    if rank == 0:
-        path = os.path.join(ROOT, 'bear_b200', 'data', 'ysd1_lag_5_file_0_preshuf.tsv')
-        epochs = 10000
+    # ---- C1: bundled ysd1 lag-5 table, end to end from the TSV (parse -> upload -> 10 000 Adam steps -> evaluation);
+    #      under torchrun every rank parses the file and keeps its slice of the one 1365-row batch (dataloader shards)
+    path = os.path.join(ROOT, 'bear_b200', 'data', 'ysd1_lag_5_file_0_preshuf.tsv')
+    epochs = 10000
 
-        def c1():
-            data = dl.KmerDataset(dl.KmerTable.from_file(path, 'dna', 3), 1500)
-            K = data.table.num_rows
-            torch.manual_seed(10)
-            params, h_signed, ar_func = bear_net.train(data.repeat(epochs), K, epochs, 0, 'dna', 5, ar_funcs.make_ar_func_linear, {},
-                                                       0.01, 'Adam', False)
-            ev = bear_net.evaluation(data, 0, 1, 'dna', torch.exp(h_signed), ar_func, np.array([0.1, 1.0, 10.0]), seed=1)
-            torch.cuda.synchronize()
-            return K, float(ev[3])
-        c1()
+    def c1():
+        data = dl.dataloader(path, 'dna', 1500, 3)
+        K = 1365
+        torch.manual_seed(10)
+        params, h_signed, ar_func = bear_net.train(data.repeat(epochs), K, epochs, 0, 'dna', 5, ar_funcs.make_ar_func_linear, {},
+                                                   0.01, 'Adam', False)
+        ev = bear_net.evaluation(data, 0, 1, 'dna', torch.exp(h_signed), ar_func, np.array([0.1, 1.0, 10.0]), seed=1)
+        torch.cuda.synchronize()
+        return K, float(ev[3])
+    c1()
+    barrier(c)
+    t0 = time.perf_counter()
+    K, perp = c1()
+    dt = max_over_ranks(c, time.perf_counter() - t0)
+    ent = {'workload': 'C1 linear BEAR lag 5 on the bundled ysd1 table (1365 rows, 3 groups), bear_lin_bear.cfg: TSV -> pack -> '
+                       '%d Adam steps of one 1365-row batch -> heldout evaluation' % epochs,
+           'seconds_end_to_end_from_tsv': dt, 'rows_per_s': K * (epochs + 1) / dt, 'heldout_perplexity_bear': perp,
+           'roofline': {'bound': 'launch latency (1365 rows per step)', 'frac': None}}
+    if cpu:
+        from oracle import bear_oracle as O
+        ce = 300
+
+        def c1_cpu():
+            kms, cnt = O.read_tsv(path, 3)
+            oh = O.one_hot(kms)
+            gen = torch.Generator().manual_seed(10)
+            params = O.init_linear(5, 4, gen)
+            hs = torch.zeros((), dtype=torch.float64)
+            O.train([(oh, torch.tensor(cnt[:, 0]))] * ce, len(kms), 'linear', params, hs, 0.01, False)
+            f = O.ar_linear(oh, params)
+            O.evaluation([(oh, f, torch.tensor(cnt[:, 1]), torch.tensor(cnt[:, 0]))], torch.exp(hs), np.array([0.1, 1.0, 10.0]))
         t0 = time.perf_counter()
-        K, perp = c1()
-        dt = time.perf_counter() - t0
-        ent = {'workload': 'C1 linear BEAR lag 5 on the bundled ysd1 table (1365 rows, 3 groups), bear_lin_bear.cfg: TSV -> pack -> '
-                           '%d Adam steps of one 1365-row batch -> heldout evaluation' % epochs,
-               'seconds_end_to_end_from_tsv': dt, 'rows_per_s': K * (epochs + 1) / dt, 'heldout_perplexity_bear': perp,
-               'roofline': {'bound': 'launch latency (1365 rows per step)', 'frac': None}}
-        if cpu:
-            from oracle import bear_oracle as O
-            ce = 300
-
-            def c1_cpu():
-                kms, cnt = O.read_tsv(path, 3)
-                oh = O.one_hot(kms)
-                gen = torch.Generator().manual_seed(10)
-                params = O.init_linear(5, 4, gen)
-                hs = torch.zeros((), dtype=torch.float64)
-                O.train([(oh, torch.tensor(cnt[:, 0]))] * ce, len(kms), 'linear', params, hs, 0.01, False)
-                f = O.ar_linear(oh, params)
-                O.evaluation([(oh, f, torch.tensor(cnt[:, 1]), torch.tensor(cnt[:, 0]))], torch.exp(hs), np.array([0.1, 1.0, 10.0]))
-            t0 = time.perf_counter()
-            c1_cpu()
-            cdt = time.perf_counter() - t0
-            ent['cpu_baseline'] = {'value': K * (ce + 1) / cdt, 'unit': 'k-mer transition rows/s', 'cores': os.cpu_count() or 1,
-                                   'kind': 'port', 'sample': 'the same TSV end to end, %d Adam steps instead of %d' % (ce, epochs)}
-        out['C1'] = ent
+        c1_cpu()
+        cdt = time.perf_counter() - t0
+        ent['cpu_baseline'] = {'value': K * (ce + 1) / cdt, 'unit': 'k-mer transition rows/s', 'cores': os.cpu_count() or 1,
+                               'kind': 'port', 'sample': 'the same TSV end to end, %d Adam steps instead of %d' % (ce, epochs)}
+    out['C1'] = ent
     barrier(c)
 
     # ---- C2: bear_ref (empirical reference transitions, stop net), lag 10, all 4^10 k-mers, evaluation only ----

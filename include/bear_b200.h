@@ -199,6 +199,27 @@ int bear_eval_step(const uint64_t* d_kmers, const uint32_t* d_test_col, const ui
                    const double* d_h /* [H] */, int H, const double* d_van /* [V] */, int V,
                    int64_t seed, int64_t row_id0, double* d_acc, double* d_workspace, void* stream);
 
+/* One fused training step of a reference-based model with the stop net (bear_ref._train_step, bear_ref.py:207-259, with
+ * make_ar_func_stop: the configs bear_stop_bear.cfg / bear_stop_ar.cfg): head f = (nw stop + JC(ref, tau)) / (nw + 1)
+ * (bear_ref.py:9-69), Dirichlet-multinomial (train_ar = 0) or multinomial (1) log-likelihood of the data column and the
+ * analytic backward in ONE pass over the two columns (40 B per row, no k-mers, no f array in memory):
+ *   d_flat[0] += loss = -scale * sum_k ll_k;  d_flat[1..3] += d loss / d [h_signed, tau_signed, net_weight_signed].
+ * d_ll_out (nullable, [n]) receives the per-k-mer log-likelihoods. */
+int bear_ref_train_step(const uint32_t* d_col, const uint32_t* d_ref_col, int64_t stride, int64_t row0, int64_t n,
+                        const double* d_h_signed, const double* d_tau_signed, const double* d_nw_signed, double scale,
+                        int train_ar, double* d_flat, double* d_ll_out, double* d_workspace, void* stream);
+
+/* The same evaluation for a reference-based model (bear_ref._evaluation_step / evaluation, bear_ref.py:391-539) in ONE
+ * kernel: the head f = (nw g(k) + JC(ref, tau)) / (nw + 1) of bear_ref.py:9-69 (Jukes-Cantor mix of the reference
+ * column's counts; nw = exp(*d_nw_signed), tau = exp(*d_tau_signed)) is evaluated in registers, no f array exists in
+ * memory.  net = BEAR_HEAD_STOP (g = stop vector, d_mat and d_kmers unused) or BEAR_HEAD_LINEAR (g = linear head of
+ * d_mat[lag, A1, A1] on the k-mers).  Other arguments as bear_eval_step. */
+int bear_ref_eval_step(const uint64_t* d_kmers, const uint32_t* d_test_col, const uint32_t* d_train_col,
+                       const uint32_t* d_ref_col, int64_t stride, int64_t row0, int64_t n, int lag, int net,
+                       const double* d_mat, const double* d_tau_signed, const double* d_nw_signed,
+                       const double* d_h /* [H] */, int H, const double* d_van /* [V] */, int V,
+                       int64_t seed, int64_t row_id0, double* d_acc, double* d_workspace, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Device: the CNN autoregressive head (ar_funcs.make_ar_func_cnn, ar_funcs.py:49-99) fused with the
  * loss: conv1d as a gather -> layer norm -> elu -> dense (FP64 tensor cores) -> layer norm -> elu ->

@@ -84,6 +84,35 @@ def test_bear_ref_evaluation_matches_oracle(cuda):
                        [-152712571.34208855, -152709051.39618367, -152745386.2824309], rtol=1e-11)
 
 
+@pytest.mark.parametrize('lag,train_col', [(7, -1), (13, 0)])
+def test_bear_ref_evaluation_linear_net_fused_matches_oracle(cuda, lag, train_col):
+    """bear_ref.evaluation with a linear embedded net runs in the fused kernel (bear_ref_eval_step, reference head in
+    registers, bear_ref.py:63-68 + 391-437); checked on a synthetic table with start-padded k-mers, ragged batches and a
+    sparse reference column."""
+    from bear_b200 import ar_funcs, bear_ref, dataloader as dl
+    from test_gpu_parity import synth_table
+    O = _oracle()
+    K = 2500
+    codes, counts = synth_table(K, lag, 3, seed=50 + lag, start_frac=0.2)
+    counts[:, 2] = np.random.default_rng(lag).poisson(0.4, size=(K, 5))
+    data = dl.KmerDataset(dl.KmerTable.from_arrays((codes, lag), counts, 'dna'), 777)
+    torch.manual_seed(lag)
+    params, h_signed, ar_func = bear_ref._create_params(lag, 4, ar_funcs.make_ar_func_linear, {})
+    params[3].mul_(30.0)
+    params[2].fill_(0.3)                           # net weight e^0.3: the net matters next to the reference counts
+    van = np.array([0.5, 2.0])
+    oh = O.one_hot(dl.decode_kmers(codes, lag, 'dna'))
+    refc = O.ref_counts_map(counts[:, 2].astype(np.float64), 4)
+    f = O.ar_ref(oh, refc, params[1].cpu(), params[2].cpu(), lambda x: O.ar_linear(x, [params[3].cpu()]), 4)
+    test_col = 1
+    got = bear_ref.evaluation(data, train_col, test_col, 2, 'dna', 0.37, ar_func, van, seed=-1)
+    want = O.evaluation([(oh, f, counts[:, test_col].astype(np.float64),
+                          counts[:, train_col].astype(np.float64) if train_col >= 0 else None)],
+                        torch.tensor(0.37, dtype=torch.float64), van)
+    for g, w in zip(got, want):
+        assert rel_err(g.numpy(), w.numpy()) <= 1e-10
+
+
 # ------------------------------------------------------------------------------------------------
 # sampler + get_var_probs
 # ------------------------------------------------------------------------------------------------
