@@ -117,6 +117,8 @@ def build(force=False, verbose=False):
         logs[src] = proc.stdout + proc.stderr
         if proc.returncode != 0:
             return obj, logs[src]
+        with open(obj + '.log', 'w') as fh:                  # ptxas -v output of this unit (registers, spills)
+            fh.write(logs[src])
         with open(stamp, 'w') as fh:
             fh.write(tag)
         return obj, None
@@ -138,8 +140,8 @@ def build(force=False, verbose=False):
         raise RuntimeError('nvcc failed linking libbear_b200.so')
     with open(os.path.join(OBJ, 'ptxas.log'), 'w') as fh:      # registers / spills per kernel, for tools/ and profiles/
         for src in SOURCES:
-            if src in logs:
-                fh.write('## %s\n%s' % (src, logs[src]))
+            if os.path.exists(os.path.join(OBJ, src + '.o.log')):
+                fh.write('## %s\n%s' % (src, open(os.path.join(OBJ, src + '.o.log')).read()))
     if library_digest() != digest:
         raise RuntimeError('libbear_b200.so was built but does not report the expected source digest')
     return LIB

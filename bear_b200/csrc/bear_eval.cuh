@@ -146,7 +146,11 @@ __device__ __noinline__ double van_dense_row(CountVec<A1> cv, double rn, double 
 
 // warps per CTA: 16 for the common call (one h, up to four priors); the eight-model variants (h_scan, many priors) keep
 // 16 + 16 running accumulators per thread and run 8 warps with up to 255 registers instead of spilling
-__host__ __device__ constexpr int ev_warps(int NH, int NV) { return (NH <= 1 && NV <= 4) ? 16 : 8; }
+#ifndef BEAR_EV_WARPS
+#define BEAR_EV_WARPS 16
+#endif
+__host__ __device__ constexpr int ev_warps(int NH, int NV) { return (NH <= 1 && NV <= 4) ? BEAR_EV_WARPS : 8; }
+__host__ __device__ constexpr int ev_ctas(int NH, int NV) { return (NH <= 1 && NV <= 4) ? 16 / BEAR_EV_WARPS : 1; }
 constexpr int EV_MAX_NW = 16;
 constexpr int EV_MAX_STAGES = 4;
 
@@ -174,10 +178,10 @@ __host__ __device__ constexpr EvalLayout eval_layout(bool lin, int nch, int nm, 
 
 // NH / NV bound the number of h values (H) and of BMM priors (V) of one launch.
 template <int HEAD, int NH, int NV, bool HAS_TRAIN>
-__global__ void __launch_bounds__(32 * ev_warps(NH, NV), 1)
+__global__ void __launch_bounds__(32 * ev_warps(NH, NV), ev_ctas(NH, NV))
 eval_tile_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ test_col, const uint32_t* __restrict__ train_col,
                  const uint32_t* __restrict__ ref_col, int64_t stride, int64_t row_lo, int64_t row_hi, int64_t row_id0, int lag,
-                 const ChunkKeys ck, int nstage, int use_tma, const double* __restrict__ head, const double* __restrict__ tau_signed,
+                 const ChunkKeys ck, const HeadGeom hg, int nstage, int use_tma, const double* __restrict__ head, const double* __restrict__ tau_signed,
                  const double* __restrict__ nw_signed, const double* __restrict__ d_h, int H, const double* __restrict__ d_van, int V,
                  int64_t seed, double* __restrict__ partials) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -328,10 +332,13 @@ eval_tile_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict_
                 if (REF) rc[b] = ok ? __ldg(ref_col + b * stride + arow) : 0u;
             }
         }
-        const bool in_range = arow >= row_lo && arow < row_hi;
-        if (!in_range) {
+        bool in_range = true;
+        if (t == 0 || t >= t_full) {                // only the first and the tail tile can hold rows outside the batch
+            in_range = arow >= row_lo && arow < row_hi;
+            if (!in_range) {
 #pragma unroll
-            for (int b = 0; b < A1; ++b) r.c[b] = 0u;
+                for (int b = 0; b < A1; ++b) r.c[b] = 0u;
+            }
         }
         r.cmax = max(max(max(r.c[0], r.c[1]), max(r.c[2], r.c[3])), r.c[4]);
         if (r.cmax < (1u << 29))
@@ -357,7 +364,7 @@ eval_tile_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict_
         if (LIN) {
 #pragma unroll
             for (int b = 0; b < A1; ++b) f[b] = 0.2;
-            if (live) linear_head_ext(R, head, code, lag, ck, nch, f);
+            if (live) linear_head_geom<0>(R, head, code, lag, hg, nch, f);
         } else {
 #pragma unroll
             for (int b = 0; b < A1; ++b)
@@ -511,7 +518,7 @@ int launch_one(const bear_eval::EvalArgs& a) {
     const int lag = LIN ? a.lag : 1;
     const int nch = num_chunks(lag);
     int nstage = EV_MAX_STAGES;
-    while (nstage > 2 && size_t(eval_layout(LIN, nch, NM, STAGE, nstage, EV_NW).total) > size_t(227 * 1024)) --nstage;
+    while (nstage > 2 && size_t(eval_layout(LIN, nch, NM, STAGE, nstage, EV_NW).total) > size_t(227 * 1024) / ev_ctas(NH, NV)) --nstage;
     const size_t smem = size_t(eval_layout(LIN, nch, NM, STAGE, nstage, EV_NW).total);
     // bulk copies need 16-byte aligned planes (tiles start at absolute multiples of 32 rows)
     auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
@@ -520,10 +527,11 @@ int launch_one(const bear_eval::EvalArgs& a) {
     const int64_t a0 = a.row0 & ~int64_t(31);
     const int64_t ntiles = (a.row0 + a.n - a0 + 31) / 32;
     const int64_t want = (ntiles + EV_NW - 1) / EV_NW;
-    const int grid = int(want < 148 ? want : 148);
+    const int cap = 148 * ev_ctas(NH, NV);
+    const int grid = int(want < cap ? want : cap);
     BEAR_CUDA_CHECK(cudaFuncSetAttribute(eval_tile_kernel<HEAD, NH, NV, HAS_TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     eval_tile_kernel<HEAD, NH, NV, HAS_TRAIN><<<grid, 32 * EV_NW, smem, a.stream>>>(
-        a.kmers, a.test_col, a.train_col, a.ref_col, a.stride, a.row0, a.row0 + a.n, a.row_id0, lag, make_chunk_keys(lag), nstage,
+        a.kmers, a.test_col, a.train_col, a.ref_col, a.stride, a.row0, a.row0 + a.n, a.row_id0, lag, make_chunk_keys(lag), make_head_geom(lag), nstage,
         use_tma, a.head_ptr, a.tau_signed, a.nw_signed, a.d_h, a.H, a.d_van, a.V, a.seed, a.ws);
     BEAR_LAUNCH_CHECK("eval_tile_kernel");
     return grid;

@@ -21,10 +21,12 @@
 #include "bear_host.h"
 #include "bear_eval.cuh"
 #include "bear_linear_head.cuh"
+#include "bear_sm100.cuh"
 
 namespace {
 
 using namespace bear;
+using namespace bear::sm100;
 
 // ------------------------------------------------------------------------------------------------
 // explicit head: f in, d loss / d f out
@@ -179,9 +181,11 @@ ref_stop_train_kernel(const uint32_t* __restrict__ col, const uint32_t* __restri
 // ------------------------------------------------------------------------------------------------
 // BMM marginal likelihood, every group and alpha
 // ------------------------------------------------------------------------------------------------
+constexpr int BMM_WARPS = 16, BMM_STAGES = 3;
+
 template <int NA1, int NV>
-__global__ void __launch_bounds__(THREADS, NA1 == 5 ? 4 : 1)
-bmm_kernel(const uint32_t* __restrict__ counts, int64_t stride, int64_t n, int G,
+__global__ void __launch_bounds__(32 * BMM_WARPS, 1)
+bmm_kernel(const uint32_t* __restrict__ counts, int64_t stride, int64_t row_lo, int64_t row_hi, int G, int use_tma,
            const double* __restrict__ d_alpha, int V, double* __restrict__ partials) {
     __shared__ double red[32];
     __shared__ double tab[NV][TABN];      // lgamma(a + c) - lgamma(a)
@@ -253,32 +257,76 @@ bmm_kernel(const uint32_t* __restrict__ counts, int64_t stride, int64_t n, int G
             }
         }
     };
-    // four rows per thread with 128-bit loads when the column is 16-byte aligned (row0 % 4 == 0)
-    const bool vec = (reinterpret_cast<uintptr_t>(col) & 15) == 0 && (stride & 3) == 0;
-    const int64_t nq = vec ? n / 4 : 0;
-    for (int64_t qd = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; qd < nq; qd += int64_t(gridDim.x) * blockDim.x) {
-        uint4 v[NA1];
-#pragma unroll
-        for (int b = 0; b < NA1; ++b) v[b] = __ldg(reinterpret_cast<const uint4*>(col + b * stride) + qd);
-        uint32_t c[NA1];
-#pragma unroll
-        for (int b = 0; b < NA1; ++b) c[b] = v[b].x;
-        row_term(c);
-#pragma unroll
-        for (int b = 0; b < NA1; ++b) c[b] = v[b].y;
-        row_term(c);
-#pragma unroll
-        for (int b = 0; b < NA1; ++b) c[b] = v[b].z;
-        row_term(c);
-#pragma unroll
-        for (int b = 0; b < NA1; ++b) c[b] = v[b].w;
-        row_term(c);
+    // Tiles of BT rows aligned to absolute multiples of BT (planes of BT * 4 bytes, 16-byte aligned); every warp is an
+    // independent pipeline over its tiles with a ring of BMM_STAGES shared-memory stages that its first NA1 lanes fill
+    // with 1-D bulk async copies (TMA), completion on an mbarrier.  NA1 = 5: BT = 128, a lane evaluates four rows from
+    // one 128-bit shared-memory load per plane.  Rows outside [row_lo, row_hi) are dead; the tail tile uses guarded loads.
+    constexpr int RPL = NA1 == 5 ? 4 : 1;                 // rows per lane
+    constexpr int BT = 32 * RPL, PLANE = BT * 4, STAGE = NA1 * PLANE;
+    extern __shared__ __align__(128) unsigned char bmm_smem[];
+    __shared__ __align__(8) uint64_t bars[BMM_WARPS * BMM_STAGES];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t my_in = smem_u32(bars) + 8 * warp * BMM_STAGES;
+    const uint32_t ring = smem_u32(bmm_smem) + warp * BMM_STAGES * STAGE;
+    if (lane == 0) {
+        for (int s = 0; s < BMM_STAGES; ++s) mbar_init(my_in + 8 * s, 1);
+        mbar_fence_init();
     }
-    for (int64_t i = nq * 4 + int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
-        uint32_t c[NA1];
+    __syncwarp();
+    const int64_t a0 = row_lo - row_lo % BT;
+    const uint32_t ntiles = uint32_t((row_hi - a0 + BT - 1) / BT);
+    const uint32_t t_full = use_tma ? uint32_t((row_hi - a0) / BT) : 0u;
+    const uint32_t tstep = gridDim.x * BMM_WARPS;
+    uint32_t t = blockIdx.x * BMM_WARPS + warp;
+    const uint32_t n_my = t < ntiles ? (ntiles - t + tstep - 1) / tstep : 0u;
+    auto issue_tile = [&](uint32_t ti, int stg) {          // lanes 0 .. NA1-1: one plane each
+        const uint32_t bar = my_in + 8 * stg;
+        if (lane == 0) mbar_arrive_expect_tx(bar, STAGE);
+        bulk_g2s(ring + stg * STAGE + lane * PLANE, col + lane * stride + a0 + int64_t(ti) * BT, PLANE, bar);
+    };
+    if (lane < NA1) {
+        for (int s = 0; s < BMM_STAGES; ++s)
+            if (uint32_t(s) < n_my && t + s * tstep < t_full) issue_tile(t + s * tstep, s);
+    }
+    int stg = 0;
+    uint32_t in_par = 0;
+    for (uint32_t it = 0; it < n_my; ++it, t += tstep) {
+        const int64_t r0 = a0 + int64_t(t) * BT + lane * RPL;          // first row of this lane
+        uint32_t cc[RPL][NA1];
+        if (t < t_full) {
+            mbar_wait(my_in + 8 * stg, in_par);
+            const uint32_t st = ring + stg * STAGE + lane * (4 * RPL);
 #pragma unroll
-        for (int b = 0; b < NA1; ++b) c[b] = __ldg(col + b * stride + i);
-        row_term(c);
+            for (int b = 0; b < NA1; ++b) {
+                if (RPL == 4) {
+                    uint32_t x, y, z, w;
+                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x), "=r"(y), "=r"(z), "=r"(w) : "r"(st + b * PLANE));
+                    cc[0][b] = x;
+                    cc[1 % RPL][b] = y;
+                    cc[2 % RPL][b] = z;
+                    cc[3 % RPL][b] = w;
+                } else {
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(cc[0][b]) : "r"(st + b * PLANE));
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < RPL; ++j)
+#pragma unroll
+                for (int b = 0; b < NA1; ++b) cc[j][b] = r0 + j < row_hi ? __ldg(col + b * stride + r0 + j) : 0u;
+        }
+        __syncwarp();
+        if (lane < NA1 && it + BMM_STAGES < n_my && t + BMM_STAGES * tstep < t_full) issue_tile(t + BMM_STAGES * tstep, stg);
+        if (++stg == BMM_STAGES) {
+            stg = 0;
+            in_par ^= 1u;
+        }
+        const bool edge = t == 0 || t >= t_full;
+#pragma unroll
+        for (int j = 0; j < RPL; ++j) {
+            if (edge && (r0 + j < row_lo || r0 + j >= row_hi)) continue;
+            row_term(cc[j]);
+        }
     }
     for (int k = 0; k < V; ++k) {
         const double s = block_sum(acc[k], red);
@@ -399,13 +447,23 @@ extern "C" int bear_bmm_likelihood(const uint32_t* d_counts, int64_t stride, int
     BEAR_REQUIRE(A1v == 5 || A1v == 21, fn);
     if (n == 0) return BEAR_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const dim3 grid(grid_for(n), G);
-    if (A1v == 5 && V <= 4)
-        bmm_kernel<5, 4><<<grid, THREADS, 0, st>>>(d_counts + row0, stride, n, G, d_alpha, V, d_workspace);
-    else if (A1v == 5)
-        bmm_kernel<5, 8><<<grid, THREADS, 0, st>>>(d_counts + row0, stride, n, G, d_alpha, V, d_workspace);
-    else
-        bmm_kernel<21, 8><<<grid, THREADS, 0, st>>>(d_counts + row0, stride, n, G, d_alpha, V, d_workspace);
+    const int bt = A1v == 5 ? 128 : 32;                       // rows per tile (bmm_kernel)
+    const int64_t a0 = row0 - row0 % bt, ntiles = (row0 + n - a0 + bt - 1) / bt;
+    const int64_t want = (ntiles + BMM_WARPS - 1) / BMM_WARPS;
+    const int gx = int(want < 148 ? want : 148);
+    const dim3 grid(gx, G);
+    const int use_tma = (reinterpret_cast<uintptr_t>(d_counts) & 15) == 0 && (stride & 3) == 0;
+    const size_t smem = size_t(BMM_WARPS) * BMM_STAGES * A1v * bt * 4;
+    if (A1v == 5 && V <= 4) {
+        BEAR_CUDA_CHECK(cudaFuncSetAttribute(bmm_kernel<5, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        bmm_kernel<5, 4><<<grid, 32 * BMM_WARPS, smem, st>>>(d_counts, stride, row0, row0 + n, G, use_tma, d_alpha, V, d_workspace);
+    } else if (A1v == 5) {
+        BEAR_CUDA_CHECK(cudaFuncSetAttribute(bmm_kernel<5, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        bmm_kernel<5, 8><<<grid, 32 * BMM_WARPS, smem, st>>>(d_counts, stride, row0, row0 + n, G, use_tma, d_alpha, V, d_workspace);
+    } else {
+        BEAR_CUDA_CHECK(cudaFuncSetAttribute(bmm_kernel<21, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        bmm_kernel<21, 8><<<grid, 32 * BMM_WARPS, smem, st>>>(d_counts, stride, row0, row0 + n, G, use_tma, d_alpha, V, d_workspace);
+    }
     BEAR_LAUNCH_CHECK("bmm_kernel");
     reduce_partials_kernel<<<1, 64, 0, st>>>(d_workspace, int(grid.x), G * V, 1.0, d_out);
     BEAR_LAUNCH_CHECK("reduce_partials_kernel");

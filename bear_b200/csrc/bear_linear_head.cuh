@@ -169,6 +169,62 @@ __device__ __forceinline__ void linear_head_ext(const double* R, const double* _
     }
 }
 
+
+// Chunk geometry of the head tables, precomputed on the host (kernel parameter: its fields are constant-bank operands):
+// chunk ch covers positions [c0, c0 + rr) and its key sits `sh` bits above the low end of the packed k-mer.
+struct HeadGeom {
+    uint8_t sh[8], rr[8], c0[8];
+};
+
+inline HeadGeom make_head_geom(int lag) {
+    HeadGeom hg;
+    const int nch = num_chunks(lag);
+    for (int ch = 0; ch < 8; ++ch) {
+        const ChunkGeom cg = chunk_geom(lag, nch, ch < nch ? ch : nch - 1);
+        hg.rr[ch] = uint8_t(cg.size);
+        hg.c0[ch] = uint8_t(cg.start);
+        hg.sh[ch] = uint8_t(2 * (lag - cg.start - cg.size));
+    }
+    return hg;
+}
+
+// softmax(sum_j mat[j, s_j, :]) of one k-mer as the normalised product of its chunk-table rows, with the chunk loop fully
+// unrolled over the precomputed geometry (NCH > 0: compile-time chunk count; NCH = 0: up to 8 chunks, `nch` at run time).
+// Rows are 32 bytes; the two 16-byte halves are swapped when bit 2 of the key is set (half_swizzle).
+template <int NCH>
+__device__ __forceinline__ void linear_head_geom(const double* R, const double* __restrict__ mat, uint64_t code, int lag,
+                                                 const HeadGeom& hg, int nch, double (&f)[A1]) {
+    const int ns = int(code >> 58);
+    const uint64_t v5 = (code & PAYLOAD_MASK) << 5;
+    double p0 = 1.0, p1 = 1.0, p2 = 1.0, p3 = 1.0;
+#pragma unroll
+    for (int ch = 0; ch < (NCH ? NCH : 8); ++ch) {
+        if (!NCH && ch >= nch) break;
+        const int rr = hg.rr[ch];
+        uint32_t q32 = uint32_t(v5 >> hg.sh[ch]) & (((1u << (2 * rr)) - 1u) << 5);     // 32 * key
+        if (ns > hg.c0[ch]) q32 = uint32_t(ext_key(q32 >> 5, rr, ns - hg.c0[ch])) << 5;
+        const uint32_t o = q32 | ((q32 >> 3) & 16u);
+        const unsigned char* row = reinterpret_cast<const unsigned char*>(R) + ch * (ENT * 32);
+        const double2 a = *reinterpret_cast<const double2*>(row + o);
+        const double2 b = *reinterpret_cast<const double2*>(row + (o ^ 16u));
+        p0 *= a.x;
+        p1 *= a.y;
+        p2 *= b.x;
+        p3 *= b.y;
+    }
+    const double z = 1.0 + ((p0 + p1) + (p2 + p3));
+    if (z < 1e300 && z > 1e-300) {
+        const double zi = 1.0 / z;
+        f[0] = p0 * zi;
+        f[1] = p1 * zi;
+        f[2] = p2 * zi;
+        f[3] = p3 * zi;
+        f[4] = zi;
+    } else {
+        linear_head_exact(mat, code, lag, f);
+    }
+}
+
 struct RowIn {
     uint64_t code;
     uint32_t c[A1];

@@ -131,8 +131,6 @@ __device__ __noinline__ void flush_accumulators(uint32_t tmem, uint32_t used, in
     }
 }
 
-// chunk geometry of the head tables, precomputed on the host: chunk ch covers positions [c0, c0 + rr) and its key sits
-// `sh` bits above the low end of the packed k-mer
 // running product of many rows' likelihood factors; its binary exponent moves to an integer before it can overflow
 struct LogProdOnly {
     double mul = 1.0;
@@ -154,10 +152,6 @@ struct LogProdOnly {
         mul *= m;
     }
     __device__ __forceinline__ double value() const { return double(ex) * 0.69314718055994530942 + (mul == 1.0 ? 0.0 : log(mul)); }
-};
-
-struct HeadGeom {
-    uint8_t sh[8], rr[8], c0[8];
 };
 
 #ifdef BEAR_T3_MAXNREG
@@ -299,37 +293,9 @@ linear_train_tc_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __res
                     issue_tile(t + nstage * tstep, stg);     // refill this stage with the tile `nstage` iterations ahead
                 const int ns = int(code >> 58);
                 const uint64_t v = code & PAYLOAD_MASK;
-                // ---- head: product of chunk-table rows (row = 32 bytes, halves swapped when bit 2 of the key is set) ----
+                // ---- head: product of chunk-table rows ----
                 double f[A1];
-                {
-                    double p0 = 1.0, p1 = 1.0, p2 = 1.0, p3 = 1.0;
-                    const uint64_t v5 = v << 5;
-#pragma unroll
-                    for (int ch = 0; ch < NCH; ++ch) {
-                        const int rr = hg.rr[ch];
-                        uint32_t q32 = uint32_t(v5 >> hg.sh[ch]) & (((1u << (2 * rr)) - 1u) << 5);     // 32 * key
-                        if (ns > hg.c0[ch]) q32 = uint32_t(ext_key(q32 >> 5, rr, ns - hg.c0[ch])) << 5;
-                        const uint32_t o = q32 | ((q32 >> 3) & 16u);
-                        const unsigned char* row = reinterpret_cast<const unsigned char*>(R) + ch * (ENT * 32);
-                        const double2 a = *reinterpret_cast<const double2*>(row + o);
-                        const double2 b = *reinterpret_cast<const double2*>(row + (o ^ 16u));
-                        p0 *= a.x;
-                        p1 *= a.y;
-                        p2 *= b.x;
-                        p3 *= b.y;
-                    }
-                    const double z = 1.0 + ((p0 + p1) + (p2 + p3));
-                    if (z < 1e300 && z > 1e-300) {
-                        const double zi = 1.0 / z;
-                        f[0] = p0 * zi;
-                        f[1] = p1 * zi;
-                        f[2] = p2 * zi;
-                        f[3] = p3 * zi;
-                        f[4] = zi;
-                    } else {
-                        linear_head_exact(mat, code, lag, f);
-                    }
-                }
+                linear_head_geom<NCH>(R, mat, code, lag, hg, NCH, f);
                 // ---- likelihood and its gradient with respect to the logits ----
                 double g[4], ll_row = 0.0;
                 {
@@ -596,13 +562,7 @@ extern "C" int bear_linear_train_step(const uint64_t* d_kmers, const uint32_t* d
     const int64_t ntiles = (row0 + n - a0 + 31) / 32;
     const int64_t want = (ntiles + T3_NPROD - 1) / T3_NPROD;
     const int grid = int(want < 148 ? want : 148);
-    HeadGeom hg;
-    for (int ch = 0; ch < 8; ++ch) {
-        const ChunkGeom cg = chunk_geom(lag, nch, ch < nch ? ch : nch - 1);
-        hg.rr[ch] = uint8_t(cg.size);
-        hg.c0[ch] = uint8_t(cg.start);
-        hg.sh[ch] = uint8_t(2 * (lag - cg.start - cg.size));
-    }
+    const HeadGeom hg = make_head_geom(lag);
     const int rc = train_ar ? launch_train_nch<true>(nch, grid, smem, st, d_kmers, d_col, stride, row0, row0 + n, lag, ck, hg, nstage,
                                                      use_tma, d_mat, d_h_signed, d_ll_out, d_workspace)
                             : launch_train_nch<false>(nch, grid, smem, st, d_kmers, d_col, stride, row0, row0 + n, lag, ck, hg, nstage,

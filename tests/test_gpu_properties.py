@@ -161,3 +161,33 @@ def test_sorted_table_matches_oracle_and_is_additive(cuda):
     b = train_step(big, 0, 0, 300000, mat.to(cuda), hs.reshape(1).to(cuda)) + \
         train_step(big, 0, 300000, (1 << 20) - 300000, mat.to(cuda), hs.reshape(1).to(cuda))
     assert float((a - b).abs().max()) <= 1e-11 * float(a.abs().max())
+
+
+@pytest.mark.parametrize('regime', [0, 1])
+def test_bmm_and_evaluation_are_additive_over_ragged_row_ranges(cuda, regime):
+    """The streaming kernels work on tiles aligned to absolute multiples of 32 / 128 rows fetched by the TMA engine; a
+    batch may start and end anywhere.  Splitting a table at odd offsets (first tile partly dead, guarded tail tile,
+    batches shorter than a tile) must give the same sums as one call, and the integer accuracy counts exactly."""
+    from bear_b200 import _lib
+    from bear_b200._lib import lib, check, ptr
+    K, lag, G = 100_003, 11, 2
+    table = synth(cuda, K, lag, G, regime)
+    k, c = table.device_tensors()
+    alpha = torch.tensor([0.3, 1.0, 7.0], dtype=torch.float64, device=cuda)
+    ws = torch.empty(lib.bear_workspace_doubles(K, lag, 0), dtype=torch.float64, device=cuda)
+    mat = (torch.randn(lag, 5, 5, dtype=torch.float64, device=cuda) * 0.3).contiguous()
+    h = torch.tensor([0.7], dtype=torch.float64, device=cuda)
+
+    def run(cuts):
+        bmm = torch.zeros((G, 3), dtype=torch.float64, device=cuda)
+        ev = torch.zeros(2 + 6 + 3, dtype=torch.float64, device=cuda)
+        for lo, hi in zip(cuts[:-1], cuts[1:]):
+            check(lib.bear_bmm_likelihood(ptr(c), table.stride, lo, hi - lo, G, 5, ptr(alpha), 3, ptr(bmm), ptr(ws), _lib.stream()))
+            check(lib.bear_eval_step(ptr(k), table.col_ptr(0), table.col_ptr(1), table.stride, lo, hi - lo, lag, _lib.HEAD_LINEAR,
+                                     ptr(mat), ptr(h), 1, ptr(alpha), 3, 99, lo, ptr(ev), ptr(ws), _lib.stream()))
+        return bmm.cpu(), ev.cpu()
+    whole_b, whole_e = run([0, K])
+    parts_b, parts_e = run([0, 1, 17, 127, 129, 4097, 33333, 33334, 77777, K - 5, K])
+    assert torch.allclose(whole_b, parts_b, rtol=1e-12, atol=0)
+    assert torch.allclose(whole_e[:5], parts_e[:5], rtol=1e-12, atol=0)
+    assert torch.equal(whole_e[5:], parts_e[5:])

@@ -5,6 +5,14 @@ cd "$(dirname "$0")/.."
 name=$1; shift
 mkdir -p bear_b200/_variants
 S=bear_b200/csrc
-nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo --std=c++17 -Xcompiler -fPIC -shared -I include -I $S "$@" \
-  -o bear_b200/_variants/libbear_$name.so $S/bear_pack.cpp $S/bear_dense.cu $S/bear_fused.cu $S/bear_train.cu $S/bear_heads.cu $S/bear_count.cu $S/bear_cnn.cu
+SRCS=$(python -c "from bear_b200 import build; print(' '.join('$S/' + s for s in build.SOURCES))")
+pids=""; objs=""
+for f in $SRCS; do
+  o=/tmp/variant_${name}_$(basename $f).o
+  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo --std=c++17 -Xcompiler -fPIC -I include -I $S "$@" -c $f -o $o &
+  pids="$pids $!"; objs="$objs $o"
+done
+for p in $pids; do wait $p; done
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o bear_b200/_variants/libbear_$name.so $objs
+rm -f $objs
 echo built bear_b200/_variants/libbear_$name.so
