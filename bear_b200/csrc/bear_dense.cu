@@ -28,25 +28,39 @@ __device__ __forceinline__ int decode_symbol(uint64_t code, int j, int lag, int 
     return j < nstart ? 4 : int((code >> (2 * (lag - 1 - j))) & 3u);
 }
 
-// core.tf_one_hot (core.py:156-174) from packed codes.  One thread per pair of output doubles so that a
-// warp writes 512 contiguous bytes (the output is 40 * lag bytes per k-mer, all of it stores).
-__global__ void decode_onehot_kernel(const uint64_t* __restrict__ kmers, int64_t n, int lag, int alphabet, int A1,
-                                     double* __restrict__ out) {
-    const int64_t per_row = int64_t(lag) * A1;
-    const int64_t total = n * per_row;
-    const int64_t pairs = (total + 1) / 2;
-    for (int64_t pidx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; pidx < pairs; pidx += int64_t(gridDim.x) * blockDim.x) {
-        double v[2];
+// core.tf_one_hot (core.py:156-174) from packed codes.  A warp owns tiles of 32 k-mers: one coalesced load of the codes,
+// then the tile's 32 * lag * A1 doubles are written as consecutive 16-byte pairs (the output is 40 * lag bytes per DNA
+// k-mer, all of it stores).  Index arithmetic is 32-bit inside a tile: row = pair element / (lag * A1) through an exact
+// float reciprocal (elements < 2^13), position / letter through division by the compile-time alphabet size.
+template <int A1>
+__global__ void __launch_bounds__(THREADS)
+decode_onehot_kernel(const uint64_t* __restrict__ kmers, int64_t n, int lag, int alphabet, double* __restrict__ out) {
+    const int per_row = lag * A1;
+    const float inv = 1.0f / float(per_row);
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t(gridDim.x) * blockDim.x) >> 5, w0 = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t ntiles = (n + 31) >> 5;
+    for (int64_t t = w0; t < ntiles; t += warps) {
+        const int64_t i0 = t << 5;
+        const int rows = int(n - i0 < 32 ? n - i0 : 32);
+        const uint64_t mine = lane < rows ? __ldg(kmers + i0 + lane) : 0ull;
+        double* dst = out + i0 * per_row;                       // 256 * per_row bytes per full tile: 16-byte aligned
+        const int total = rows * per_row;
+        for (int base = 0; base < total; base += 64) {          // uniform trip count: every lane takes part in the shuffles
+            const int e = base + 2 * lane;
+            double v[2];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int64_t e = 2 * pidx + h;
-            const int64_t i = e / per_row;
-            const int r = int(e - i * per_row);
-            const int j = r / A1, b = r - j * A1;
-            v[h] = (e < total && decode_symbol(__ldg(kmers + (i < n ? i : n - 1)), j, lag, alphabet) == b) ? 1.0 : 0.0;
+            for (int h = 0; h < 2; ++h) {
+                const int x = e + h;
+                const int row = min(__float2int_rz((float(x) + 0.5f) * inv), 31);
+                const int r = x - row * per_row;
+                const int j = r / A1, b = r - j * A1;
+                const uint64_t code = __shfl_sync(0xffffffffu, mine, row);
+                v[h] = (x < total && decode_symbol(code, j, lag, alphabet) == b) ? 1.0 : 0.0;
+            }
+            if (e + 1 < total) *reinterpret_cast<double2*>(dst + e) = make_double2(v[0], v[1]);
+            else if (e < total) dst[e] = v[0];
         }
-        if (2 * pidx + 1 < total) *reinterpret_cast<double2*>(out + 2 * pidx) = make_double2(v[0], v[1]);
-        else out[2 * pidx] = v[0];
     }
 }
 
@@ -60,15 +74,32 @@ __global__ void decode_symbols_kernel(const uint64_t* __restrict__ kmers, int64_
     }
 }
 
-// group-planar uint32 [G][A1][stride] -> dense float64 [n, G, A1] (the tensor of dataloader.py:44-46)
-__global__ void unpack_counts_kernel(const uint32_t* __restrict__ counts, int64_t stride, int64_t n, int G, int A1,
-                                     double* __restrict__ out) {
-    const int GA = G * A1;
-    const int64_t total = n * GA;
-    for (int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += int64_t(gridDim.x) * blockDim.x) {
-        const int64_t i = idx / GA;
-        const int p = int(idx - i * GA);
-        out[idx] = double(counts[int64_t(p) * stride + i]);
+// group-planar uint32 [G][A1][stride] -> dense float64 [n, G, A1] (the tensor of dataloader.py:44-46).  A warp owns
+// tiles of 32 rows: it reads the G * A1 planes with coalesced 128-byte loads into a shared-memory tile [row][plane]
+// (row pitch odd: conflict-free) and writes the tile's 32 * G * A1 doubles as one contiguous run.  GROUPWISE (tiles too
+// wide for shared memory: many protein groups): one group at a time, runs of A1 doubles.
+template <int A1, bool GROUPWISE>
+__global__ void __launch_bounds__(THREADS)
+unpack_counts_kernel(const uint32_t* __restrict__ counts, int64_t stride, int64_t n, int G, double* __restrict__ out) {
+    extern __shared__ uint32_t unpack_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t warps = (int64_t(gridDim.x) * blockDim.x) >> 5, w0 = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t ntiles = (n + 31) >> 5;
+    const int GA = G * A1, W = GROUPWISE ? A1 : GA, pitch = W | 1;
+    uint32_t* tile = unpack_smem + warp * 32 * pitch;
+    for (int64_t t = w0; t < ntiles; t += warps) {
+        const int64_t i0 = t << 5;
+        const int rows = int(n - i0 < 32 ? n - i0 : 32);
+        for (int g = 0; g < (GROUPWISE ? G : 1); ++g) {
+            const uint32_t* src = counts + int64_t(g) * A1 * stride + i0 + lane;
+            for (int p = 0; p < W; ++p) tile[lane * pitch + p] = lane < rows ? __ldg(src + p * stride) : 0u;
+            __syncwarp();
+            for (int e = lane; e < rows * W; e += 32) {
+                const int r = e / W, p = e - r * W;
+                out[(i0 + r) * GA + g * A1 + p] = double(tile[r * pitch + p]);
+            }
+            __syncwarp();
+        }
     }
 }
 
@@ -353,7 +384,11 @@ extern "C" int bear_decode_onehot(const uint64_t* d_kmers, int64_t n, int lag, i
     BEAR_REQUIRE(bear_alphabet_size(alphabet) > 0 && lag >= 1 && lag <= bear_max_lag(alphabet) && n >= 0, fn);
     if (n == 0) return BEAR_OK;
     BEAR_REQUIRE(d_kmers && d_onehot, fn);
-    decode_onehot_kernel<<<blocks_for((n * lag * (bear_alphabet_size(alphabet) + 1) + 1) / 2), THREADS, 0, ST(stream)>>>(d_kmers, n, lag, alphabet, bear_alphabet_size(alphabet) + 1, d_onehot);
+    const int grid = blocks_for(n, 148 * 8);                     // one warp per 32 k-mers
+    if (alphabet == BEAR_ALPHABET_PROT)
+        decode_onehot_kernel<21><<<grid, THREADS, 0, ST(stream)>>>(d_kmers, n, lag, alphabet, d_onehot);
+    else
+        decode_onehot_kernel<5><<<grid, THREADS, 0, ST(stream)>>>(d_kmers, n, lag, alphabet, d_onehot);
     BEAR_LAUNCH_CHECK("decode_onehot_kernel");
     return BEAR_OK;
 }
@@ -371,10 +406,24 @@ extern "C" int bear_decode_symbols(const uint64_t* d_kmers, int64_t n, int lag, 
 extern "C" int bear_unpack_counts(const uint32_t* d_counts, int64_t stride, int64_t row0, int64_t n, int G, int A1,
                                   double* d_out, void* stream) {
     const char* fn = "bear_unpack_counts";
-    BEAR_REQUIRE(n >= 0 && row0 >= 0 && stride >= row0 + n && G >= 1 && A1 >= 2, fn);
+    BEAR_REQUIRE(n >= 0 && row0 >= 0 && stride >= row0 + n && G >= 1 && (A1 == 5 || A1 == 21), fn);
     if (n == 0) return BEAR_OK;
     BEAR_REQUIRE(d_counts && d_out, fn);
-    unpack_counts_kernel<<<blocks_for(n * G * A1), THREADS, 0, ST(stream)>>>(d_counts + row0, stride, n, G, A1, d_out);
+    const int grid = blocks_for(n, 148 * 8);                     // one warp per 32 rows
+    const bool wide = G * A1 > 80;                               // whole-row tiles up to 8 DNA groups / 3 protein groups
+    const size_t smem = size_t(THREADS / 32) * 32 * ((wide ? A1 : G * A1) | 1) * sizeof(uint32_t);
+    const uint32_t* src = d_counts + row0;
+    if (A1 == 5 && !wide) {
+        BEAR_CUDA_CHECK(cudaFuncSetAttribute(unpack_counts_kernel<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        unpack_counts_kernel<5, false><<<grid, THREADS, smem, ST(stream)>>>(src, stride, n, G, d_out);
+    } else if (A1 == 5) {
+        unpack_counts_kernel<5, true><<<grid, THREADS, smem, ST(stream)>>>(src, stride, n, G, d_out);
+    } else if (!wide) {
+        BEAR_CUDA_CHECK(cudaFuncSetAttribute(unpack_counts_kernel<21, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        unpack_counts_kernel<21, false><<<grid, THREADS, smem, ST(stream)>>>(src, stride, n, G, d_out);
+    } else {
+        unpack_counts_kernel<21, true><<<grid, THREADS, smem, ST(stream)>>>(src, stride, n, G, d_out);
+    }
     BEAR_LAUNCH_CHECK("unpack_counts_kernel");
     return BEAR_OK;
 }

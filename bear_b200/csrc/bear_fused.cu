@@ -211,6 +211,28 @@ bmm_kernel(const uint32_t* __restrict__ counts, int64_t stride, int64_t row_lo, 
         tab_tot[k][idx % TABN] = t.add + (t.mul == 1.0 ? 0.0 : log(t.mul));
     }
     __syncthreads();
+    // Sparse rows (every count <= 8, total <= 16; the rule in k-mer tables of whole genomes): the likelihood is a linear
+    // function of the HISTOGRAM of the counts -- sum_rows sum_b T_k[c_b] = sum_c hist[c] T_k[c] -- whatever the priors, so
+    // a row only bumps integer histogram bins: 8-bit fields of 64-bit registers (counts 1..8, totals 1..16), spilled
+    // into per-lane 32-bit bins before a field can overflow.  No table look-ups, no float arithmetic per row; the bins
+    // meet the tables once, at the end.  Integer bins also make the result independent of the order of the rows.
+    uint64_t hl = 0, ht0 = 0, ht1 = 0;                     // packed fields: letters with count f + 1, totals f + 1 / f + 9
+    uint32_t bin_l[8], bin_t[16];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bin_l[j] = 0u;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) bin_t[j] = 0u;
+    int pending = 0;                                       // rows since the last spill (uniform over the warp)
+    auto spill_fields = [&]() {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            bin_l[j] += uint32_t(hl >> (8 * j)) & 0xffu;
+            bin_t[j] += uint32_t(ht0 >> (8 * j)) & 0xffu;
+            bin_t[8 + j] += uint32_t(ht1 >> (8 * j)) & 0xffu;
+        }
+        hl = ht0 = ht1 = 0;
+        pending = 0;
+    };
     auto row_term = [&](const uint32_t (&c)[NA1]) {
         uint32_t cmax = 0, toti = 0;
 #pragma unroll
@@ -219,7 +241,13 @@ bmm_kernel(const uint32_t* __restrict__ counts, int64_t stride, int64_t row_lo, 
             toti += c[b] < uint32_t(TABN) ? c[b] : uint32_t(TABN);
         }
         if (cmax == 0) return;
-        if (toti < uint32_t(TABN)) {
+        if (NA1 == 5 && cmax <= 8u && toti <= 16u) {
+#pragma unroll
+            for (int b = 0; b < NA1; ++b)
+                if (c[b] != 0u) hl += 1ull << (8u * (c[b] - 1u));
+            if (toti <= 8u) ht0 += 1ull << (8u * (toti - 1u));
+            else ht1 += 1ull << (8u * (toti - 9u));
+        } else if (toti < uint32_t(TABN)) {
 #pragma unroll
             for (int k = 0; k < NV; ++k) {
                 if (k < V) {
@@ -326,6 +354,20 @@ bmm_kernel(const uint32_t* __restrict__ counts, int64_t stride, int64_t row_lo, 
         for (int j = 0; j < RPL; ++j) {
             if (edge && (r0 + j < row_lo || r0 + j >= row_hi)) continue;
             row_term(cc[j]);
+        }
+        pending += RPL;
+        if (pending > 255 / NA1 - RPL) spill_fields();     // a field grows by at most NA1 per row
+    }
+    spill_fields();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        if (k < V) {
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s += double(bin_l[j]) * tab[k][j + 1];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) s -= double(bin_t[j]) * tab_tot[k][j + 1];
+            acc[k] += s;
         }
     }
     for (int k = 0; k < V; ++k) {
