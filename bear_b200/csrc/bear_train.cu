@@ -12,10 +12,10 @@
 //     64-bit fixed point (power-of-two scale chosen per tile from the largest |g| in it, four scale classes 2^12 apart) and
 //     split into eight balanced base-256 digits; the warp writes the digits (B operand, 32 rows x 32 int8) and the one-hot
 //     rows (A operand, 128 (position, letter) rows x 32 k-mers, uint8) into its shared-memory slab in the canonical
-//     MN-major layout and publishes a sequence byte; one thread of warp 15 polls the 15 bytes with a single 128-bit
-//     load and issues one tcgen05.mma (kind::i8, M 128 x N 32 x K 32) per staged tile into the tensor-memory
-//     accumulator of the tile's scale class (issuing a tcgen05.mma stalls the issuing warp for > 100 cycles, so the
-//     row pipelines do not issue their own).  Integer sums are order-independent: no atomics, no ranking of equal keys,
+//     MN-major layout and publishes a sequence byte; warp 15 polls the status bytes (lane w watches pipeline w, ballots
+//     make the ready set warp-uniform) and issues one tcgen05.mma (kind::i8, M 128 x N 32 x K 32) per staged tile into
+//     the tensor-memory accumulator of the tile's scale class (a tcgen05.mma blocks its issuing thread for ~140 cycles:
+//     the row pipelines do not issue their own).  Integer sums are order-independent: no atomics, no ranking of equal keys,
 //     bit-reproducible.  Every 2^21 rows per CTA (and at the end) the S32 accumulators are read back (tcgen05.ld),
 //     recombined and added to float64 totals.  The start symbol's gradient is (sum over all rows) - (sum over the four
 //     letters), taken on the integer digit sums.
@@ -38,7 +38,12 @@ using namespace bear::sm100;
 #endif
 constexpr int T3_THREADS = BEAR_T3_THREADS;
 constexpr int T3_NW = T3_THREADS / 32;
-constexpr int T3_NPROD = T3_NW - 1;        // warps 0..14 compute rows, warp 15 issues the tensor-core work
+// A tcgen05.mma of this size blocks its issuing thread for ~140 cycles whatever the shape, and several threads can issue
+// concurrently (tools/probe/umma_rate3.cu: 139 / 70 / 40 cycles per product with 1 / 2 / 4 issuers, unaffected by the other
+// warps' shared-memory or float64 traffic).  One issuing warp is enough as long as its own instruction stream is short:
+// with per-lane descriptors nvcc wraps every tcgen05 instruction in an ELECT / R2UR uniformisation loop and a product cost
+// 400-480 cycles of the issuer (the bound of the kernel); with ballots and elect.sync it is a handful of uniform ALU ops.
+constexpr int T3_NPROD = T3_NW - 1;        // warps 0 .. T3_NPROD-1 compute rows, the last warp issues the tensor-core work
 constexpr int SLAB_A = 4096;               // one-hot operand of a tile: 8 groups of 16 (position, letter) rows x 32 k-mers
 constexpr int SLAB_B = 1024;               // digit operand of a tile: 2 groups of 16 digit columns x 32 k-mers
 constexpr int STAGE_BYTES = 256 + A1 * 128;   // k-mer plane + five count planes of a 32-row tile
@@ -49,7 +54,7 @@ constexpr uint32_t TMEM_COLS = 128;        // NCLS accumulators of 32 columns
 constexpr uint64_t DIGIT_BIAS = 0x0080808080808080ull;
 
 struct Train3Layout {                      // offsets in bytes from the start of dynamic shared memory
-    int R, slab_a, slab_b, ring, acc, acc_start, ones, tab_lg, tab_dg, stir, symtab, red, bars, misc, total;
+    int R, slab_a, slab_b, ring, run, acc, acc_start, ones, tab_lg, tab_dg, stir, symtab, red, bars, misc, total;
 };
 
 __host__ __device__ constexpr Train3Layout train3_layout(int nch, int nstage) {
@@ -59,6 +64,7 @@ __host__ __device__ constexpr Train3Layout train3_layout(int nch, int nstage) {
     o = (o + 127) & ~127;
     L.slab_a = o;     o += T3_NPROD * SLAB_A;
     L.slab_b = o;     o += T3_NPROD * SLAB_B;
+    L.run = o;        o += 4 * T3_THREADS * 8;   // per-thread running sums [4][threads]: kept out of the register file
     L.acc = o;        o += 128 * 4 * 8;          // [(position, letter) row][logit] float64 totals
     L.acc_start = o;  o += 32 * 4 * 8;           // [position][logit] totals of the start symbol
     L.ones = o;       o += 32 * 4;               // digit sums of the all-rows operand row (one scale class at a time)
@@ -68,7 +74,7 @@ __host__ __device__ constexpr Train3Layout train3_layout(int nch, int nstage) {
     L.symtab = o;     o += 2 * ENT * 2;
     L.red = o;        o += 32 * 8;
     L.bars = o;       o += (T3_NPROD + T3_NPROD * MAX_STAGES + 1) * 8;
-    L.misc = o;       o += 48;                   // [0] tmem base [1] classes in use [2] non-finite flag; +16: 32 slab status bytes
+    L.misc = o;       o += 64;                   // [0] tmem base [1] non-finite flag [2] classes in use; +32: 32 slab status bytes
     o = (o + 127) & ~127;
     L.ring = o;       o += T3_NPROD * nstage * STAGE_BYTES;      // last: every other offset is independent of nstage
     L.total = o;
@@ -159,6 +165,9 @@ struct LogProdOnly {
 #else
 #define BEAR_T3_BOUNDS __launch_bounds__(T3_THREADS, 1)
 #endif
+#ifdef BEAR_T3_DEBUG
+__device__ unsigned long long g_t3_dbg[8];      // issuer: [0] loop cycles [1] issue cycles [2] sweeps [3] empty sweeps [4] products
+#endif
 template <bool TRAIN_AR, int NCH>
 __global__ void BEAR_T3_BOUNDS
 linear_train_tc_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ col, int64_t stride, int64_t row_lo,
@@ -179,7 +188,7 @@ linear_train_tc_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __res
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + L.bars);
     volatile uint32_t* misc = reinterpret_cast<volatile uint32_t*>(smem_raw + L.misc);
     // status byte of warp w's slab: (tiles staged so far) << 2 | scale class of the staged tile
-    volatile uint8_t* slab_status = reinterpret_cast<volatile uint8_t*>(smem_raw + L.misc + 16);
+    volatile uint8_t* slab_status = reinterpret_cast<volatile uint8_t*>(smem_raw + L.misc + 32);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double hval = exp(h_signed[0]), hinv = exp(-h_signed[0]);   // h = exp(h_signed)  (bear_net.py:186) and 1 / h
@@ -205,9 +214,7 @@ linear_train_tc_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __res
         }
         mbar_init(bar_done, 1);
         mbar_fence_init();
-        misc[1] = 0u;
-        misc[2] = 0u;
-        for (int i = 4; i < 12; ++i) misc[i] = 0u;           // slab status bytes
+        for (int i = 1; i < 16; ++i) misc[i] = 0u;           // flags and slab status bytes
     }
     if (warp == T3_NPROD) tmem_alloc(smem_u32(const_cast<uint32_t*>(&misc[0])), TMEM_COLS);
     build_ext_tables(mat, R, symtab, lag, ck);
@@ -228,8 +235,13 @@ linear_train_tc_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __res
     const int64_t rest = int64_t(ntiles) - (int64_t(niter - 1) * gridDim.x + blockIdx.x) * T3_NPROD;
     const int nlast = rest < 0 ? 0 : rest > T3_NPROD ? T3_NPROD : int(rest);
 
-    double acc_add = 0.0, dh_sum = 0.0;
-    LogProdOnly acc_prod;
+    // per-thread running sums (log-likelihood: additive part and product part; d ll / d h_signed) live in shared memory:
+    // one load / store pair per tile instead of seven registers held across the whole float64 section
+    double* run = reinterpret_cast<double*>(smem_raw + L.run) + threadIdx.x;
+    run[0] = 0.0;                       // additive part of the log-likelihood
+    run[T3_THREADS] = 0.0;              // d ll / d h_signed
+    run[2 * T3_THREADS] = 1.0;          // running product of likelihood factors
+    run[3 * T3_THREADS] = 0.0;          // its binary exponent
     uint32_t flushes = 0;
 
     if (warp < T3_NPROD) {
@@ -337,7 +349,7 @@ linear_train_tc_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __res
                         double Wh = 0.0;
 #pragma unroll
                         for (int b = 0; b < A1; ++b) Wh = fma(conc[b] - BEAR_EPS, w[b], Wh);
-                        if (live) dh_sum -= Wh - tdg * hinv;    // d ll / d h_signed = -sum_b f_b d ll/d f_b
+                        if (live) run[T3_THREADS] -= Wh - tdg * hinv;    // d ll / d h_signed = -sum_b f_b d ll/d f_b
                         const double W = Wh * hval;
 #pragma unroll
                         for (int b = 0; b < 4; ++b) g[b] = (conc[b] - BEAR_EPS) * (w[b] - W);
@@ -345,10 +357,15 @@ linear_train_tc_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __res
                     if (live) {
                         if (ll_out) {
                             ll_row = add + log(prod);
-                            acc_add += ll_row;
+                            run[0] += ll_row;
                         } else {
-                            acc_add += add;
+                            run[0] += add;
+                            LogProdOnly acc_prod;
+                            acc_prod.mul = run[2 * T3_THREADS];
+                            acc_prod.ex = 0;
                             acc_prod.push(0.0, prod);
+                            run[2 * T3_THREADS] = acc_prod.mul;
+                            if (acc_prod.ex != 0) run[3 * T3_THREADS] += double(acc_prod.ex);
                         }
                     }
                 }
@@ -366,13 +383,16 @@ linear_train_tc_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __res
                 hmax = __reduce_max_sync(0xffffffffu, hmax);
                 const int ex = int(hmax >> 20) - 1023;       // floor(log2 max|g|);  |g| <= row total < 2^35 by construction
                 const int cls = ex < 6 ? 0 : ex < 18 ? 1 : ex < 30 ? 2 : 3;
-                if (ex >= 42 && lane == 0) misc[2] = 1u;     // inf / nan (diverged parameters): the gradient is reported as nan
+                if (ex >= 42 && lane == 0) misc[1] = 1u;     // inf / nan (diverged parameters): the gradient is reported as nan
                 const double scale = __hiloint2double((1023 + 56 - 12 * cls) << 20, 0);
                 uint64_t z[4];
 #pragma unroll
                 for (int b = 0; b < 4; ++b)
                     z[b] = (uint64_t(__double2ll_rn(g[b] * scale)) + DIGIT_BIAS) ^ DIGIT_BIAS;   // balanced base-256 digits
                 // ---- operands of the tile's tensor-core product ----
+#ifdef BEAR_T3_EXP_NOSLAB
+                if (z[0] + z[1] + z[2] + z[3] == 0x123456789abcdefull) misc[1] = 1u;   // (experiment: math only)
+#else
                 if (it > 0) mbar_wait(bar_empty + 8 * warp, (it - 1) & 1u);   // the previous product has read the slab
                 {
                     // one-hot rows m = 4 j + s (letters s of position j); the zero padding below the last position makes
@@ -411,6 +431,7 @@ linear_train_tc_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __res
                     __threadfence_block();
                     slab_status[warp] = uint8_t(((it + 1) << 2) | uint32_t(cls));
                 }
+#endif
             }
             if (++stg == nstage) {
                 stg = 0;
@@ -422,65 +443,93 @@ linear_train_tc_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __res
                 tc_fence_before();
                 __syncthreads();
                 tc_fence_after();
-                flush_accumulators(tmem, misc[1], lag, acc, acc_start, ones);
+                flush_accumulators(tmem, misc[2], lag, acc, acc_start, ones);
                 tc_fence_before();
                 __syncthreads();
             }
         }
     } else {
         // ---------------- tensor-core issuer: one product per staged tile, whichever warp is ready ----------------
+        // The whole warp runs this loop converged: lane w watches the status byte of row pipeline w, the set of ready
+        // pipelines and their scale classes are ballots (warp-uniform values, held in uniform registers), and the
+        // tcgen05 instructions are issued under elect.sync -- no per-lane descriptors, no uniformisation loops.
         const uint32_t idesc = umma_idesc_i8(128, 32);
         const uint64_t desc_a0 = umma_desc(smem_u32(smem_raw + L.slab_a), 128, 512);
         const uint64_t desc_b0 = umma_desc(smem_u32(smem_raw + L.slab_b), 128, 512);
-        const uint32_t status_addr = smem_u32(smem_raw + L.misc + 16);
-        constexpr int NSW = (T3_NPROD + 3) / 4;              // status words
-        uint32_t seen[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};   // last status bytes acted upon
+        const uint32_t status_addr = smem_u32(smem_raw + L.misc + 32) + (lane < T3_NPROD ? lane : 0);
+        uint32_t seen = 0;                                   // lane w: last status byte of pipeline w acted upon
         for (uint32_t it0 = 0; it0 < niter; it0 += FLUSH_IT) {
             const uint32_t it1 = it0 + FLUSH_IT < niter ? it0 + FLUSH_IT : niter;
-            if (lane == 0) {
-                uint32_t cls_used = 0;                      // accumulators written since the last read-back
-                // products still to issue in this window (only the very last iteration can be ragged)
-                uint32_t remaining = (it1 - it0) * T3_NPROD - (it1 == niter ? uint32_t(T3_NPROD - nlast) : 0u);
-                while (remaining) {
-                    uint32_t cur[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-                    asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                                 : "=r"(cur[0]), "=r"(cur[1]), "=r"(cur[2]), "=r"(cur[3]) : "r"(status_addr) : "memory");
-                    if (NSW > 4)
-                        asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                                     : "=r"(cur[4]), "=r"(cur[5]), "=r"(cur[6]), "=r"(cur[7]) : "r"(status_addr + 16) : "memory");
-                    uint32_t diff = 0;
-#pragma unroll
-                    for (int i = 0; i < NSW; ++i) diff |= cur[i] ^ seen[i];
-                    if (diff == 0u) {
-                        __nanosleep(64);
-                        continue;
-                    }
-                    __threadfence_block();                  // the status bytes were written after the slabs
-                    tc_fence_after();
-#pragma unroll
-                    for (int w = 0; w < T3_NPROD; ++w) {
-                        const uint32_t st = (cur[w >> 2] >> (8 * (w & 3))) & 0xffu;
-                        if (st != ((seen[w >> 2] >> (8 * (w & 3))) & 0xffu)) {
-                            const uint32_t cls = st & 3u;
-                            umma_i8(tmem + cls * 32, desc_a0 + uint64_t(w * (SLAB_A >> 4)), desc_b0 + uint64_t(w * (SLAB_B >> 4)), idesc,
-                                    (cls_used >> cls) & 1u);
-                            cls_used |= 1u << cls;
-                            umma_commit(bar_empty + 8 * w);
-                            --remaining;
-                        }
-                    }
-#pragma unroll
-                    for (int i = 0; i < NSW; ++i) seen[i] = cur[i];
+            uint32_t cls_used = 0;                          // accumulators written since the last read-back
+            // products still to issue in this window (only the very last iteration can be ragged)
+            uint32_t remaining = (it1 - it0) * T3_NPROD - (it1 == niter ? uint32_t(T3_NPROD - nlast) : 0u);
+#ifdef BEAR_T3_EXP_NOSLAB
+            remaining = 0;
+#endif
+#ifdef BEAR_T3_DEBUG
+            unsigned long long d_issue = 0, d_sweeps = 0, d_empty = 0;
+            const long long d_t0 = clock64();
+#endif
+            while (remaining) {
+                uint32_t st;
+                asm volatile("ld.volatile.shared.u8 %0, [%1];" : "=r"(st) : "r"(status_addr) : "memory");
+                if (lane >= T3_NPROD) st = 0u;
+                const uint32_t ready = __ballot_sync(0xffffffffu, st != seen);
+#ifdef BEAR_T3_DEBUG
+                ++d_sweeps;
+#endif
+                if (ready == 0u) {
+#ifdef BEAR_T3_DEBUG
+                    ++d_empty;
+#endif
+                    __nanosleep(32);
+                    continue;
                 }
-                umma_commit(bar_done);
-                mbar_wait(bar_done, flushes & 1u);
-                misc[1] = cls_used;
+#ifdef BEAR_T3_DEBUG
+                const long long d_i0 = clock64();
+#endif
+                seen = st;
+                const uint32_t c0 = __ballot_sync(0xffffffffu, (st & 1u) != 0u), c1 = __ballot_sync(0xffffffffu, (st & 2u) != 0u);
+                __threadfence_block();                      // the status bytes were written after the slabs
+                tc_fence_after();
+                uint32_t m = ready;
+                while (m) {
+                    const uint32_t w = uint32_t(__ffs(int(m))) - 1u;
+                    m &= m - 1u;
+                    const uint32_t cls = ((c0 >> w) & 1u) | (((c1 >> w) & 1u) << 1);
+                    if (elect_one()) {
+#ifdef BEAR_T3_EXP_NOMMA
+                        mbar_arrive(bar_empty + 8 * w);      // (experiment: no tensor-core product)
+#else
+                        umma_i8(tmem + cls * 32, desc_a0 + uint64_t(w * (SLAB_A >> 4)), desc_b0 + uint64_t(w * (SLAB_B >> 4)), idesc,
+                                (cls_used >> cls) & 1u);
+                        umma_commit(bar_empty + 8 * w);
+#endif
+                    }
+                    cls_used |= 1u << cls;
+                }
+                remaining -= uint32_t(__popc(ready));
+#ifdef BEAR_T3_DEBUG
+                d_issue += clock64() - d_i0;
+#endif
             }
+#ifdef BEAR_T3_DEBUG
+            if (lane == 0) {
+                atomicAdd(&g_t3_dbg[0], (unsigned long long)(clock64() - d_t0));
+                atomicAdd(&g_t3_dbg[1], d_issue);
+                atomicAdd(&g_t3_dbg[2], d_sweeps);
+                atomicAdd(&g_t3_dbg[3], d_empty);
+                atomicAdd(&g_t3_dbg[4], (unsigned long long)((it1 - it0) * T3_NPROD));
+            }
+#endif
+            if (elect_one()) umma_commit(bar_done);
+            mbar_wait(bar_done, flushes & 1u);
+            if (lane == 0) misc[2] = cls_used;
             ++flushes;
             tc_fence_before();
             __syncthreads();
             tc_fence_after();
-            flush_accumulators(tmem, misc[1], lag, acc, acc_start, ones);
+            flush_accumulators(tmem, misc[2], lag, acc, acc_start, ones);
             tc_fence_before();
             __syncthreads();
         }
@@ -488,9 +537,11 @@ linear_train_tc_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __res
     if (warp == T3_NPROD) tmem_dealloc(tmem, TMEM_COLS);
     const int P = 2 + lag * A1 * A1;
     double* out = partials + int64_t(blockIdx.x) * P;
-    const double ll_thread = acc_add + acc_prod.value();
+    LogProdOnly acc_prod;
+    acc_prod.mul = run[2 * T3_THREADS];
+    const double ll_thread = run[0] + (run[3 * T3_THREADS] * 0.69314718055994530942 + acc_prod.value());
     const double ll_blk = block_sum(ll_thread, red);
-    const double dh_blk = block_sum(dh_sum, red);
+    const double dh_blk = block_sum(run[T3_THREADS], red);
     if (threadIdx.x == 0) {
         out[0] = ll_blk;
         out[1] = dh_blk;
@@ -498,7 +549,7 @@ linear_train_tc_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __res
     __syncthreads();
     // d ll / d mat[j, s, b]: letters from the operand rows, the start symbol (s = 4) from its own totals; the five logit
     // gradients of a row sum to zero, which gives b = 4
-    const bool bad = misc[2] != 0u;
+    const bool bad = misc[1] != 0u;
     for (int idx = threadIdx.x; idx < lag * A1 * A1; idx += blockDim.x) {
         const int b = idx % A1, s = (idx / A1) % A1, j = idx / (A1 * A1);
         const double* src = s < 4 ? acc + (4 * j + s) * 4 : acc_start + j * 4;
@@ -529,6 +580,16 @@ int launch_train_nch(int nch, int grid, size_t smem, cudaStream_t st, const uint
 }
 
 }  // namespace
+
+#ifdef BEAR_T3_DEBUG
+extern "C" int bear_debug_t3(unsigned long long* out8) {
+    BEAR_CUDA_CHECK(cudaDeviceSynchronize());
+    BEAR_CUDA_CHECK(cudaMemcpyFromSymbol(out8, g_t3_dbg, 8 * sizeof(unsigned long long)));
+    const unsigned long long zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    BEAR_CUDA_CHECK(cudaMemcpyToSymbol(g_t3_dbg, zero, sizeof(zero)));
+    return BEAR_OK;
+}
+#endif
 
 extern "C" int64_t bear_workspace_doubles(int64_t n, int lag, int nparams) {
     (void)n;

@@ -59,6 +59,14 @@ for lag, regime, name in ((20, 0, 'lag20'), (20, 2, 'lag20-sorted'), (13, 0, 'la
         for _ in range(2):
             fn()
         torch.cuda.synchronize()
+        dbg = getattr(ctypes.CDLL(_lib.LIB_PATH), 'bear_debug_t3', None)       # built with -DBEAR_T3_DEBUG
+        if kn == 'train' and dbg is not None:
+            buf = (ctypes.c_ulonglong * 8)()
+            dbg(buf)
+            fn()
+            dbg(buf)
+            out.append('%s issuer: %.0f cycles per product in the loop, %.0f of them issuing; %.2f sweeps per product (%.2f empty)' % (
+                name, buf[0] / max(buf[4], 1), buf[1] / max(buf[4], 1), buf[2] / max(buf[4], 1), buf[3] / max(buf[4], 1)))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(5):
