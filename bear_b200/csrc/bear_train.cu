@@ -36,6 +36,9 @@ using namespace bear::sm100;
 #ifndef BEAR_T3_THREADS
 #define BEAR_T3_THREADS 512
 #endif
+#ifndef BEAR_T3_SLEEP
+#define BEAR_T3_SLEEP 32
+#endif
 constexpr int T3_THREADS = BEAR_T3_THREADS;
 constexpr int T3_NW = T3_THREADS / 32;
 // A tcgen05.mma of this size blocks its issuing thread for ~140 cycles whatever the shape, and several threads can issue
@@ -428,8 +431,9 @@ linear_train_tc_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __res
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) {
-                    __threadfence_block();
-                    slab_status[warp] = uint8_t(((it + 1) << 2) | uint32_t(cls));
+                    // release: the slab writes of the warp (ordered before this lane by the __syncwarp) precede the status byte
+                    asm volatile("st.release.cta.shared.u8 [%0], %1;" ::"r"(smem_u32(smem_raw + L.misc + 32) + warp),
+                                 "r"(((it + 1) << 2) | uint32_t(cls)) : "memory");
                 }
 #endif
             }
@@ -472,7 +476,7 @@ linear_train_tc_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __res
 #endif
             while (remaining) {
                 uint32_t st;
-                asm volatile("ld.volatile.shared.u8 %0, [%1];" : "=r"(st) : "r"(status_addr) : "memory");
+                asm volatile("ld.acquire.cta.shared.u8 %0, [%1];" : "=r"(st) : "r"(status_addr) : "memory");
                 if (lane >= T3_NPROD) st = 0u;
                 const uint32_t ready = __ballot_sync(0xffffffffu, st != seen);
 #ifdef BEAR_T3_DEBUG
@@ -482,7 +486,7 @@ linear_train_tc_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __res
 #ifdef BEAR_T3_DEBUG
                     ++d_empty;
 #endif
-                    __nanosleep(32);
+                    __nanosleep(BEAR_T3_SLEEP);
                     continue;
                 }
 #ifdef BEAR_T3_DEBUG
@@ -490,7 +494,6 @@ linear_train_tc_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __res
 #endif
                 seen = st;
                 const uint32_t c0 = __ballot_sync(0xffffffffu, (st & 1u) != 0u), c1 = __ballot_sync(0xffffffffu, (st & 2u) != 0u);
-                __threadfence_block();                      // the status bytes were written after the slabs
                 tc_fence_after();
                 uint32_t m = ready;
                 while (m) {
