@@ -150,8 +150,8 @@ __device__ __noinline__ double van_dense_row(CountVec<A1> cv, double rn, double 
 #define BEAR_EV_WARPS 16
 #endif
 __host__ __device__ constexpr int ev_warps(int NH, int NV) { return (NH <= 1 && NV <= 4) ? BEAR_EV_WARPS : 8; }
-__host__ __device__ constexpr int ev_ctas(int NH, int NV) { return (NH <= 1 && NV <= 4) ? 16 / BEAR_EV_WARPS : 1; }
-constexpr int EV_MAX_NW = 16;
+__host__ __device__ constexpr int ev_ctas(int NH, int NV) { return (NH <= 1 && NV <= 4 && BEAR_EV_WARPS <= 16) ? 16 / BEAR_EV_WARPS : 1; }
+constexpr int EV_MAX_NW = 32;
 constexpr int EV_MAX_STAGES = 4;
 
 struct EvalLayout {                  // offsets in bytes from the start of dynamic shared memory

@@ -71,6 +71,7 @@ class KmerTable:
         self.A1 = int(counts.shape[1])
         self.stride = int(counts.shape[2])
         self._dev = None
+        self._sorted = None
 
     # -- construction -------------------------------------------------------------------------
     @classmethod
@@ -120,6 +121,7 @@ class KmerTable:
         self.num_rows, self.lag, self.alphabet = int(num_rows), int(lag), alphabet
         self.num_ds, self.A1, self.stride = (int(s) for s in counts_dev.shape)
         self._dev = (kmers_dev, counts_dev)
+        self._sorted = None
         return self
 
     @classmethod
@@ -236,7 +238,17 @@ class KmerTable:
                                             ptr(k), ptr(c), self.stride, lo, _lib.stream()))
                 torch.cuda.current_stream().synchronize()  # the pinned stage is reused by the next chunk
             self._dev = (k, c)
+            self._sorted = None
         return self._dev
+
+    def sorted_index(self):
+        """(sorted packed codes, row order) of the resident table, built once per upload: every point query
+        (get_var_probs.lookup_counts, assemble) is a binary search against it instead of a fresh O(K log K) sort."""
+        k, _ = self.device_tensors()
+        if getattr(self, '_sorted', None) is None or self._sorted[0].device != k.device:
+            keys, order = torch.sort(k[:self.num_rows])
+            self._sorted = (keys, order)
+        return self._sorted
 
     def col_ptr(self, ds_loc):
         """Device address of plane 0 of count column ``ds_loc``."""

@@ -161,18 +161,28 @@ def get_pdf(kmers, counts, h, ar_func, mc_samples, vans, train_col, alphabet_nam
 
 def lookup_counts(data, kmers, alphabet_name):
     """Counts [Kq, num_ds, A1] (float64, device) of the query k-mer strings in a resident table;
-    zeros for k-mers that are absent.  One packed-code join on the device."""
+    zeros for k-mers that are absent.  One packed-code join on the device against the table's cached
+    sorted index (``KmerTable.sorted_index``); a k-mer that occurs in several rows (tables concatenated
+    from several files) gets the sum of its rows, as a counter would give."""
     table = data.table
     codes, lag = dataloader.encode_kmers(kmers, alphabet_name)
     if lag != table.lag:
         raise ValueError('query k-mers have length %d, the table has lag %d' % (lag, table.lag))
     k, c = table.device_tensors()
     q = torch.from_numpy(codes.view(np.int64)).to(k.device)
-    keys, order = torch.sort(k[:table.num_rows])
-    pos = torch.searchsorted(keys, q).clamp_(max=max(table.num_rows - 1, 0))
-    found = (keys[pos] == q) if table.num_rows else torch.zeros_like(q, dtype=torch.bool)
-    rows = order[pos]
-    out = c[:, :, rows].permute(2, 0, 1).to(torch.float64) * found[:, None, None]
+    if table.num_rows == 0:
+        found = torch.zeros_like(q, dtype=torch.bool)
+        return torch.zeros((q.numel(), c.shape[0], c.shape[1]), dtype=torch.float64, device=k.device), found
+    keys, order = table.sorted_index()
+    lo = torch.searchsorted(keys, q)
+    hi = torch.searchsorted(keys, q, right=True)
+    mult = hi - lo                                           # rows holding the k-mer
+    found = mult > 0
+    last = table.num_rows - 1
+    out = c[:, :, order[lo.clamp(max=last)]].permute(2, 0, 1).to(torch.float64) * found[:, None, None]
+    for d in range(1, int(mult.max()) if q.numel() else 0):  # repeated keys: add the other rows
+        more = mult > d
+        out += c[:, :, order[(lo + d).clamp(max=last)]].permute(2, 0, 1).to(torch.float64) * more[:, None, None]
     return out.contiguous(), found
 
 

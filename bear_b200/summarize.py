@@ -64,6 +64,10 @@ def count_kmers(seqs, groups, lag, num_groups=None, reverse=False):
     dev = _lib.device()
     groups = np.asarray(groups, dtype=np.int32)
     G = int(num_groups if num_groups is not None else (groups.max() + 1 if len(groups) else 1))
+    if len(groups) != len(seqs):
+        raise ValueError('one group id per sequence is required')
+    if len(groups) and (groups.min() < 0 or groups.max() >= G):
+        raise ValueError('group ids must lie in [0, %d)' % G)     # (they index the count table on the device)
     lens = np.array([len(s) for s in seqs], dtype=np.int64)
     offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
     toff = np.concatenate([[0], np.cumsum(lens + 1)]).astype(np.int64)
@@ -78,7 +82,8 @@ def count_kmers(seqs, groups, lag, num_groups=None, reverse=False):
     d_toff = torch.from_numpy(toff[:-1].copy()).to(dev)
     d_grp = torch.from_numpy(groups).to(dev)
     strands = 2 if reverse else 1
-    # distinct k-mers <= min(transitions, 4^lag + start-padded prefixes); keep the table at most half full
+    # distinct k-mers <= min(transitions, 4^lag + start-padded prefixes); keep the table at most half full.
+    # Device memory: cap * (8 + 20 G) bytes with cap = the next power of two above twice that bound.
     bound = min(ntrans * strands, sum(4 ** i for i in range(lag + 1)))
     cap = 1 << max(4, int(np.ceil(np.log2(2 * bound + 1))))
     keys = torch.full((cap,), -1, dtype=torch.int64, device=dev)
@@ -89,9 +94,15 @@ def count_kmers(seqs, groups, lag, num_groups=None, reverse=False):
     distinct, skipped, overflow = (int(x) for x in stats.cpu())
     if overflow:
         raise OverflowError('a transition count exceeded 2^32 - 1')
-    rows = torch.nonzero(keys != -1).reshape(-1)              # occupied slots, in slot order (deterministic)
+    rows = torch.nonzero(keys != -1).reshape(-1)              # occupied slots
     n = int(rows.numel())
     assert n == distinct
+    # The slot a key lands in depends on which thread wins a probe race, so slot order is not reproducible.  Rows go
+    # out ordered by a hash of the key instead: the same table on every run, and shuffled as the reference recommends
+    # for training (a table sorted by k-mer makes consecutive minibatches share their leading positions).
+    mixed = keys[rows] * -7046029254386353131                # 0x9E3779B97F4A7C15 (wraps)
+    mixed = mixed ^ (mixed >> 29)
+    rows = rows[torch.argsort(mixed * -4658895280553007687)]
     stride = max((n + 3) // 4 * 4, 4)
     out_k = torch.zeros(stride, dtype=torch.int64, device=dev)
     out_c = torch.zeros((G, 5, stride), dtype=torch.int32, device=dev)

@@ -409,3 +409,22 @@ def test_assemble_follows_the_counted_sequence(cuda, tmp_path):
     gen, ent = assemble.assemble_no_ends([src[:lag]], [[0, 30]], 200, None, van=1e6, lag=lag, alphabet_name='dna',
                                          data=data, reverse=True, seed=6)
     assert len(set(gen[0])) > 150 and np.all(ent[0][lag:] > 1.2) and np.allclose(ent[0][:lag], 0.0)
+
+
+def test_lookup_counts_repeated_keys_and_cached_index(cuda):
+    """A k-mer held by several rows (tables concatenated from several files) gets the sum of its rows, absent
+    k-mers get zeros, and the sorted index is built once per resident table (no sort per query)."""
+    from bear_b200 import dataloader, get_var_probs
+    rng = np.random.default_rng(5)
+    kmers = np.array(['ACGT', 'CCGT', 'ACGT', '[[AC', 'TTTT', 'ACGT', 'CCGT'])
+    counts = rng.integers(0, 50, size=(len(kmers), 2, 5))
+    table = dataloader.KmerTable.from_arrays(kmers, counts, 'dna')
+    data = dataloader.KmerDataset(table, 4)
+    query = np.array(['ACGT', 'GGGG', 'CCGT', '[[AC', 'TTTT'])
+    got, found = get_var_probs.lookup_counts(data, query, 'dna')
+    want = np.stack([counts[kmers == q].sum(axis=0) if (kmers == q).any() else np.zeros((2, 5)) for q in query])
+    assert found.cpu().tolist() == [True, False, True, True, True]
+    assert np.array_equal(got.cpu().numpy(), want.astype(np.float64))
+    index = table.sorted_index()
+    get_var_probs.lookup_counts(data, query[:2], 'dna')
+    assert table.sorted_index()[0] is index[0]              # the same tensors: nothing was re-sorted
