@@ -346,14 +346,17 @@ eval_tile_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict_
         else
             r.n = (double(r.c[0]) + double(r.c[1])) + (double(r.c[2]) + double(r.c[3])) + double(r.c[4]);
         const bool live = r.cmax != 0;             // no test transitions: contributes 0 to every output
-        const uint32_t steps = warp_steps(live, r.cmax);          // (a warp collective: every lane has read its stage)
-        __syncwarp();
-        if (lane < NPLANES && it + nstage < n_my && t + nstage * tstep < t_full)
-            issue_tile(t + nstage * tstep, stg);    // refill this stage with the tile `nstage` iterations ahead
-        if (++stg == nstage) {
-            stg = 0;
-            in_par ^= 1u;
-        }
+        const uint32_t steps = warp_steps(live, r.cmax);
+        // The test counts stay in the stage until the end of the iteration: the count at a predicted letter is one
+        // shared-memory load by index (count_at) instead of a chain of selects.  Tail tiles (guarded loads) select.
+        const bool staged = t < t_full;
+        const uint32_t cnt_addr = ring + stg * STAGE + OFF_TEST + lane * 4;
+        auto count_at = [&](int idx) -> uint32_t {
+            if (!staged) return pick5(r.c, idx);
+            uint32_t v;
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(cnt_addr + uint32_t(idx) * 128u));
+            return v;
+        };
         double tr[A1] = {0, 0, 0, 0, 0};
         if (HAS_TRAIN && live) {
 #pragma unroll
@@ -412,7 +415,7 @@ eval_tile_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict_
                 if (live) {
                     ear_add[k] += add;
                     ear_prod[k].push(0.0, prod);
-                    cor_ear[k] += pick5(r.c, noisy_argmax5(conc, 100.0 * BEAR_EPS, seed, grow, uint64_t(k)));
+                    cor_ear[k] += count_at(noisy_argmax5(conc, 100.0 * BEAR_EPS, seed, grow, uint64_t(k)));
                 }
             }
         }
@@ -425,7 +428,7 @@ eval_tile_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict_
             if (live) {
                 arm_add += add;
                 arm_prod.push(0.0, prod);
-                cor_arm += pick5(r.c, noisy_argmax5(p, BEAR_EPS, seed, grow, 100));
+                cor_arm += count_at(noisy_argmax5(p, BEAR_EPS, seed, grow, 100));
             }
         }
         // vanilla BMM: conc = train + van + eps   (bear_net.py:328-331, 339-340)
@@ -472,9 +475,16 @@ eval_tile_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict_
                         if ((k & 3) == 0) van_hash = mix64(uint64_t(seed) ^ (grow * 0x9E3779B97F4A7C15ull) ^ (uint64_t(200 + k) * 0xD1B54A32D192ED03ull));
                         best = int((uint32_t(van_hash >> (16 * (k & 3))) & 0xffffu) * 5u >> 16);
                     }
-                    cor_van[k] += pick5(r.c, best);
+                    cor_van[k] += count_at(best);
                 }
             }
+        }
+        __syncwarp();                               // every lane is done with the stage
+        if (lane < NPLANES && it + nstage < n_my && t + nstage * tstep < t_full)
+            issue_tile(t + nstage * tstep, stg);    // refill this stage with the tile `nstage` iterations ahead
+        if (++stg == nstage) {
+            stg = 0;
+            in_par ^= 1u;
         }
     }
     // layout: [ll_ear[H], ll_arm, ll_van[V], cor_ear[H], cor_arm, cor_van[V], total]
