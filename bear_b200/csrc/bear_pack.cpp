@@ -256,6 +256,30 @@ struct PackJob {
     uint64_t* kmers;
     uint32_t* counts;
     bool sparse;
+    // rank-sharded ingest (shard_batch > 0): of every global batch of shard_batch consecutive file rows this rank keeps
+    // its contiguous slice, ceil(rows of the batch / world) rows from offset rank * that (dataloader.KmerDataset.shard)
+    int64_t shard_batch = 0, total = 0;
+    int world = 1, rank = 0;
+
+    // rows of batch b (of n_b rows) owned by the rank
+    int64_t local_rows_of(int64_t n_b) const {
+        const int64_t per = (n_b + world - 1) / world;
+        const int64_t lo = std::min<int64_t>(int64_t(rank) * per, n_b), hi = std::min<int64_t>(int64_t(rank + 1) * per, n_b);
+        return hi - lo;
+    }
+    // output row of file row g, or -1 when the row belongs to another rank / lies outside the window
+    int64_t out_row_of(int64_t g) const {
+        if (shard_batch <= 0) {
+            const int64_t o = g - first_row;
+            return (o >= 0 && o < max_rows) ? o : -1;
+        }
+        const int64_t b = g / shard_batch, i = g - b * shard_batch;
+        const int64_t n_b = std::min<int64_t>(shard_batch, total - b * shard_batch);
+        const int64_t per = (n_b + world - 1) / world;
+        if (i / per != rank) return -1;
+        const int64_t o = b * local_rows_of(shard_batch) + (i - int64_t(rank) * per);       // batches before b are full
+        return o < max_rows ? o : -1;
+    }
 };
 
 int check_kmer(const PackJob& j, const char* s, int len, int64_t file_row, uint64_t* out) {
@@ -420,9 +444,10 @@ const char* skip_header(const char* b, const char* e, int header) {
 }
 
 int pack_file(const char* fn, const char* path, int header, int alphabet, int num_ds, int64_t first_row, int64_t max_rows,
-              uint64_t* h_kmers, uint32_t* h_counts, int64_t stride, int64_t* rows_out, int* lag_out, bool sparse) {
+              uint64_t* h_kmers, uint32_t* h_counts, int64_t stride, int64_t* rows_out, int* lag_out, bool sparse,
+              int64_t shard_batch = 0, int world = 1, int rank = 0) {
     if (!path || bear_alphabet_size(alphabet) < 0 || num_ds < 1 || first_row < 0 || max_rows < 0 || !h_kmers || !h_counts ||
-        stride < max_rows || !rows_out || !lag_out) {
+        stride < max_rows || !rows_out || !lag_out || shard_batch < 0 || world < 1 || rank < 0 || rank >= world) {
         bear_set_error("%s: bad argument", fn);
         return BEAR_ERR_ARG;
     }
@@ -438,6 +463,10 @@ int pack_file(const char* fn, const char* path, int header, int alphabet, int nu
     if (total <= first_row) return BEAR_OK;
     // the lag is the k-mer length of the first data row
     PackJob job{alphabet, num_ds, bear_alphabet_size(alphabet) + 1, 0, first_row, max_rows, stride, h_kmers, h_counts, sparse};
+    job.shard_batch = shard_batch;
+    job.total = total;
+    job.world = world;
+    job.rank = rank;
     for (const char* p = b; p < e;) {
         const char* le = line_end(p, e);
         if (!blank_line(p, le)) {
@@ -466,8 +495,8 @@ int pack_file(const char* fn, const char* path, int header, int alphabet, int nu
             for (const char* p = r.b; p < r.e;) {
                 const char* le = line_end(p, r.e);
                 if (!blank_line(p, le)) {
-                    const int64_t out_row = file_row - job.first_row;
-                    if (out_row >= job.max_rows) return;
+                    const int64_t out_row = job.out_row_of(file_row);
+                    if (job.shard_batch <= 0 && file_row - job.first_row >= job.max_rows) return;
                     if (out_row >= 0) {
                         const char* end = le;
                         while (end > p && end[-1] == '\r') --end;
@@ -491,7 +520,12 @@ int pack_file(const char* fn, const char* path, int header, int alphabet, int nu
             bear_set_error("%s", r.err.c_str());
             return r.rc;
         }
-    *rows_out = std::min(max_rows, total - first_row);
+    if (shard_batch > 0) {
+        const int64_t full = total / shard_batch, rest = total - full * shard_batch;
+        *rows_out = std::min(max_rows, full * job.local_rows_of(shard_batch) + (rest ? job.local_rows_of(rest) : 0));
+    } else {
+        *rows_out = std::min(max_rows, total - first_row);
+    }
     *lag_out = job.lag;
     return BEAR_OK;
 }
@@ -522,6 +556,17 @@ extern "C" int bear_pack_sparse(const char* path, int header, int alphabet, int 
                                 int64_t* rows_out, int* lag_out) {
     return pack_file("bear_pack_sparse", path, header, alphabet, num_ds, first_row, max_rows, h_kmers, h_counts, stride,
                      rows_out, lag_out, true);
+}
+
+extern "C" int bear_pack_shard(const char* path, int sparse, int header, int alphabet, int num_ds, int64_t batch_rows,
+                               int world, int rank, int64_t max_rows, uint64_t* h_kmers, uint32_t* h_counts, int64_t stride,
+                               int64_t* rows_out, int* lag_out) {
+    if (batch_rows < 1) {
+        bear_set_error("bear_pack_shard: bad argument");
+        return BEAR_ERR_ARG;
+    }
+    return pack_file("bear_pack_shard", path, header, alphabet, num_ds, 0, max_rows, h_kmers, h_counts, stride, rows_out, lag_out,
+                     sparse != 0, batch_rows, world, rank);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -92,6 +92,32 @@ class KmerTable:
         return cls(kmers, counts, rows.value, max(lag.value, 1), alphabet)
 
     @classmethod
+    def from_file_shard(cls, file, alphabet, num_ds, batch_size, rank, world, sparse=False, header=None):
+        """This rank's rows of a count file: of every global batch of ``batch_size`` consecutive rows the contiguous
+        slice ``KmerDataset.shard`` would give it, parsed straight from the file -- no rank ever holds (or parses the
+        numbers of) the whole table.  Returns (table, total rows of the file)."""
+        if header is None:
+            header = bool(sparse)
+        path = os.fsencode(file)
+        K = check(lib.bear_count_rows(path, int(header)))
+        A1 = ALPHABET_SIZES[alphabet] + 1
+        local = sum(n for _, n in shard_ranges(K, batch_size, rank, world)[0])
+        stride = max(_round_up(local, 4), 4)
+        kmers = np.zeros(stride, dtype=np.uint64)
+        counts = np.zeros((num_ds, A1, stride), dtype=np.uint32)
+        rows, lag = ctypes.c_int64(0), ctypes.c_int(0)
+        check(lib.bear_pack_shard(path, int(bool(sparse)), int(header), _lib.ALPHABET_IDS[alphabet], num_ds, int(batch_size),
+                                  int(world), int(rank), local, ptr(kmers), ptr(counts), stride, ctypes.byref(rows),
+                                  ctypes.byref(lag)))
+        assert rows.value == local
+        if local == 0 and K > 0:                 # a rank without rows still reports the table's lag (first row)
+            k1, c1 = np.zeros(4, dtype=np.uint64), np.zeros((num_ds, A1, 4), dtype=np.uint32)
+            fn = lib.bear_pack_sparse if sparse else lib.bear_pack_tsv
+            check(fn(path, int(header), _lib.ALPHABET_IDS[alphabet], num_ds, 0, 1, ptr(k1), ptr(c1), 4, ctypes.byref(rows),
+                     ctypes.byref(lag)))
+        return cls(kmers, counts, local, max(lag.value, 1), alphabet), K
+
+    @classmethod
     def from_arrays(cls, kmers, counts, alphabet):
         """kmers: strings or uint64 codes with ``lag`` given as (codes, lag); counts [K, G, A1] integers."""
         if isinstance(kmers, tuple):
@@ -266,6 +292,22 @@ class KmerTable:
         return decode_kmers(host, self.lag, self.alphabet)
 
 
+def shard_ranges(K, batch_size, rank, world):
+    """How a table of K rows cut into global batches of ``batch_size`` rows spreads over ``world`` ranks: rank keeps
+    the contiguous slice [rank * per, (rank + 1) * per) of every batch, per = ceil(rows of the batch / world).
+    Returns (local (row0, n) per batch, global rows per batch, global index of the first local row per batch)."""
+    ranges, grows, ids, o = [], [], [], 0
+    for r0 in range(0, K, batch_size):
+        n = min(batch_size, K - r0)
+        per = -(-n // world)
+        lo, hi = min(rank * per, n), min((rank + 1) * per, n)
+        ranges.append((o, hi - lo))
+        grows.append(n)
+        ids.append(r0 + lo)
+        o += hi - lo
+    return ranges, grows, ids
+
+
 class KmerDataset:
     """What ``dataloader`` returns: a packed table cut into minibatches of ``batch_size`` consecutive
     rows (dataloader.py:37), optionally repeated (``.repeat(epochs)``, models/train_bear_net.py:87).
@@ -356,18 +398,28 @@ def _local_shard(ds):
     return ds
 
 
+def _load_file(file, alphabet, batch_size, num_ds, sparse, header):
+    """One count file -> this process's KmerDataset.  Under ``torch.distributed`` every rank parses only its own
+    slice of every global batch (``bear_pack_shard``); nothing holds the whole table."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        rank, world = dist.get_rank(), dist.get_world_size()
+        table, K = KmerTable.from_file_shard(file, alphabet, num_ds, batch_size, rank, world, sparse=sparse, header=header)
+        ranges, grows, ids = shard_ranges(K, int(batch_size), rank, world)
+        return KmerDataset(table, batch_size, 1, ranges, grows, None, ids)
+    return KmerDataset(KmerTable.from_file(file, alphabet, num_ds, sparse=sparse, header=header), batch_size)
+
+
 def dataloader(file, alphabet, batch_size, num_ds, cache=True, header=False, n_par=1, dtype=torch.float64):
     """Dense TSV ``kmer \\t [[counts g0],[counts g1],...]`` -> KmerDataset (reference:
     dataloader.py:6-50).  ``cache`` / ``n_par`` are accepted for signature parity; the packed table is
     always resident."""
-    table = KmerTable.from_file(file, alphabet, num_ds, sparse=False, header=header)
-    return _local_shard(KmerDataset(table, batch_size))
+    return _load_file(file, alphabet, batch_size, num_ds, False, header)
 
 
 def sparse_dataloader(file, alphabet, batch_size, num_ds, cache=False, header=True, n_par=1, dtype=torch.float64):
     """Sparse ``kmer; [[g,b],...]; [v,...]`` file -> KmerDataset (reference: dataloader.py:52-109)."""
-    table = KmerTable.from_file(file, alphabet, num_ds, sparse=True, header=header)
-    return _local_shard(KmerDataset(table, batch_size))
+    return _load_file(file, alphabet, batch_size, num_ds, True, header)
 
 
 def load_files(files, alphabet, batch_size, num_ds, sparse=False, header=None):

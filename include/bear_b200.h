@@ -86,6 +86,15 @@ int bear_pack_sparse(const char* path, int header, int alphabet, int num_ds,
                      uint64_t* h_kmers, uint32_t* h_counts, int64_t stride,
                      int64_t* rows_out, int* lag_out);
 
+/* Rank-sharded ingest for data-parallel training (the reference splits every global batch over the replicas inside
+ * one process, bear_net.py:273; here every rank parses only its own rows): of every global batch of `batch_rows`
+ * consecutive file rows, rank keeps the contiguous slice [rank * per, (rank + 1) * per), per = ceil(rows of the batch /
+ * world), written densely in batch order.  sparse = 0: the dense TSV format, 1: the sparse format.  *rows_out = rows of
+ * this rank (needs max_rows and stride >= that: at most ceil(batch_rows / world) * ceil(total / batch_rows)). */
+int bear_pack_shard(const char* path, int sparse, int header, int alphabet, int num_ds, int64_t batch_rows,
+                    int world, int rank, int64_t max_rows, uint64_t* h_kmers, uint32_t* h_counts, int64_t stride,
+                    int64_t* rows_out, int* lag_out);
+
 /* n k-mer strings of length `lag`, concatenated without separators -> packed codes, and back. */
 int bear_encode_kmers(const char* h_text, int64_t n, int lag, int alphabet, uint64_t* h_kmers);
 int bear_decode_kmers(const uint64_t* h_kmers, int64_t n, int lag, int alphabet, char* h_text);

@@ -171,6 +171,29 @@ def test_dataset_batching_and_sharding_cover_every_row_once():
         assert per_batch.tolist() == [300, 300, 300, 300, 165]
 
 
+@pytest.mark.parametrize('path,sparse,num_ds', [(YSD1, False, 3), (SPARSE, True, 1)])
+def test_rank_sharded_ingest_equals_shard_of_the_full_table(path, sparse, num_ds):
+    """bear_pack_shard: every rank parses only its slice of every global batch; the result is bit-identical to
+    KmerDataset.shard() of the whole table (same rows, same order, same batch geometry and global row ids)."""
+    from bear_b200 import dataloader as dl
+    full = dl.KmerTable.from_file(path, 'dna', num_ds, sparse=sparse)
+    K = full.num_rows
+    for batch, world in ((455, 3), (100, 4), (max(K, 1), 2), (7, 5), (K + 10, 3)):
+        want_ds = dl.KmerDataset(full, batch)
+        total = 0
+        for rank in range(world):
+            t, k_file = dl.KmerTable.from_file_shard(path, 'dna', num_ds, batch, rank, world, sparse=sparse)
+            assert k_file == K and t.lag == full.lag
+            want = want_ds.shard(rank, world) if world > 1 else want_ds
+            assert t.num_rows == want.table.num_rows
+            assert np.array_equal(t.kmers_host[:t.num_rows], want.table.kmers_host[:t.num_rows])
+            assert np.array_equal(t.counts_host[:, :, :t.num_rows], want.table.counts_host[:, :, :t.num_rows])
+            ranges, grows, ids = dl.shard_ranges(K, batch, rank, world)
+            assert ranges == want.ranges and grows == want.global_rows and ids == want.row_ids
+            total += t.num_rows
+        assert total == K
+
+
 def test_packed_binary_cache_round_trip(tmp_path):
     """TSV -> BEARPACK shard -> memory-mapped table: bit-identical arrays and metadata."""
     from bear_b200 import dataloader as dl

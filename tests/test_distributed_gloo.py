@@ -1,7 +1,7 @@
 """world_size-2 CPU (gloo) test of the data-parallel host logic: row sharding of every batch, the
 global-batch loss scale, ONE allreduce of the flat [loss, d h, d params] buffer per optimizer step and
 identical updates on every rank.  The per-batch gradient is supplied by the oracle here (the CUDA
-kernels cannot run on this box); what is under test is bear_b200._engine / dataloader.shard."""
+kernels cannot run on this box); what is under test is bear_b200._engine and the rank-sharded ingest of dataloader."""
 import os
 import socket
 
@@ -27,11 +27,13 @@ def _run(rank, world, port, batch, acc_steps, out_path):
     from bear_b200 import _engine as eng, dataloader as dl
     from oracle import bear_oracle as O
     torch.set_num_threads(1)
-    data = dl.KmerDataset(dl.KmerTable.from_file(YSD1, 'dna', 3), batch)
-    K = data.table.num_rows
+    # under an initialised process group dataloader() parses only this rank's slice of every batch (bear_pack_shard)
+    data = dl.dataloader(YSD1, 'dna', batch, 3)
+    K = dl.count_rows(YSD1)
+    assert sum(g for _, _, g in data.batches()) == K
     calls = {'allreduce': 0}
     if world > 1:
-        data = data.shard(rank, world)
+        assert data.table.num_rows < K
         real = dist.all_reduce
 
         def counting(t, *a, **k):
