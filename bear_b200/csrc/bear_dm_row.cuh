@@ -65,7 +65,28 @@ __device__ __forceinline__ void rf_letters(const TS* __restrict__ stir, const do
             P[b] = 1.0;
             D[b] = 0.0;
         }
+        // The last letter is the stop symbol: about one transition per sequence, so its count is 0 or 1 in all but a
+        // few rows.  When that holds for the whole warp (one vote) it is set directly and the loop runs over the other
+        // letters only: a fifth fewer predicated float64 slots.
+        const bool last_small = !__any_sync(0xffffffffu, c[A1 - 1] > 1u);
         double kd = 0.0;
+        if (last_small) {
+            for (uint32_t k = 0; k < steps; ++k, kd += 1.0) {
+#pragma unroll
+                for (int b = 0; b < A1 - 1; ++b) {
+                    const double t = a[b] + kd;
+                    if (c[b] > k) {
+                        D[b] = fma(D[b], t, P[b]);
+                        P[b] *= t;
+                    }
+                }
+            }
+            if (c[A1 - 1] != 0u) {
+                P[A1 - 1] = a[A1 - 1];
+                D[A1 - 1] = 1.0;
+            }
+            return;
+        }
         for (uint32_t k = 0; k < steps; ++k, kd += 1.0) {
 #pragma unroll
             for (int b = 0; b < A1; ++b) {
