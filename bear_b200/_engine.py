@@ -135,7 +135,8 @@ class FlatParams:
 
 class Optimizer:
     """tf.keras.optimizers.<name>(learning_rate) with Keras (OptimizerV2) defaults, on the flat buffer
-    (bear_net.py:264-265).  Adam runs as one libbear_b200 kernel; the others are a few torch ops."""
+    (bear_net.py:264-265: ``getattr(tf.keras.optimizers, optimizer_name)``).  Adam runs as one libbear_b200 kernel; SGD,
+    RMSprop, Adagrad, Adadelta, Adamax and Nadam are a few torch ops on the flat buffer (Ftrl is not implemented)."""
 
     def __init__(self, name, learning_rate, n, device):
         self.name, self.lr = name, float(learning_rate)
@@ -149,8 +150,17 @@ class Optimizer:
             self.v = z()
         elif name == 'Adagrad':
             self.v = z() + 0.1
+        elif name == 'Adadelta':
+            self.v, self.d = z(), z()                      # accumulated squared gradients / squared updates
+        elif name == 'Adamax':
+            self.m, self.v = z(), z()                      # first moment, exponentially weighted infinity norm
+            self.t = torch.zeros((), dtype=torch.float64, device=device)
+        elif name == 'Nadam':
+            self.m, self.v = z(), z()
+            self.t = torch.zeros((), dtype=torch.float64, device=device)
+            self.msched = torch.ones((), dtype=torch.float64, device=device)     # product of the momentum schedule
         else:
-            raise ValueError("optimizer '%s' is not supported (Adam, SGD, RMSprop, Adagrad)" % name)
+            raise ValueError("optimizer '%s' is not supported (Adam, SGD, RMSprop, Adagrad, Adadelta, Adamax, Nadam)" % name)
 
     def apply(self, params, grads):
         if self.name == 'Adam':
@@ -164,6 +174,27 @@ class Optimizer:
         elif self.name == 'Adagrad':
             self.v.addcmul_(grads, grads)
             params.sub_(self.lr * grads / (self.v.sqrt() + 1e-7))
+        elif self.name == 'Adadelta':                      # rho = 0.95, epsilon = 1e-7 (Keras defaults)
+            self.v.mul_(0.95).addcmul_(grads, grads, value=0.05)
+            upd = grads * ((self.d + 1e-7).sqrt() / (self.v + 1e-7).sqrt())
+            self.d.mul_(0.95).addcmul_(upd, upd, value=0.05)
+            params.sub_(self.lr * upd)
+        elif self.name == 'Adamax':                        # beta_1 = 0.9, beta_2 = 0.999, epsilon = 1e-7
+            self.t += 1.0                                  # (step counters are device scalars: graph-capturable)
+            self.m.mul_(0.9).add_(grads, alpha=0.1)
+            torch.maximum(self.v * 0.999, grads.abs(), out=self.v)
+            params.sub_((self.lr / (1.0 - torch.pow(0.9, self.t))) * self.m / (self.v + 1e-7))
+        elif self.name == 'Nadam':                         # Keras: momentum schedule u_t = beta_1 (1 - 0.5 * 0.96^(0.004 t))
+            self.t += 1.0
+            u_t = 0.9 * (1.0 - 0.5 * torch.pow(0.96, 0.004 * self.t))
+            u_n = 0.9 * (1.0 - 0.5 * torch.pow(0.96, 0.004 * (self.t + 1.0)))
+            self.msched.mul_(u_t)
+            self.m.mul_(0.9).add_(grads, alpha=0.1)
+            self.v.mul_(0.999).addcmul_(grads, grads, value=0.001)
+            g_hat = grads / (1.0 - self.msched)
+            m_hat = self.m / (1.0 - self.msched * u_n)
+            v_hat = self.v / (1.0 - torch.pow(0.999, self.t))
+            params.sub_(self.lr * ((1.0 - u_t) * g_hat + u_n * m_hat) / (v_hat.sqrt() + 1e-7))
 
     def step_and_clear(self, fp, loss_slot, loss_scale):
         """One optimizer step on the (already allreduced) flat buffer ``fp.grad`` = [loss, grads...]: records

@@ -256,9 +256,31 @@ def h_scan(data, ds_loc_train, ds_loc_test, alphabet, h, ar_func, dtype=torch.fl
     """Evaluate a trained BEAR model at several h values (bear_net.py:465-531).
     Returns (log_likelihood_ear[H], perplexity_ear[H], accuracy_ear[H])."""
     table = eng.check_dataset(data)
-    if table.A1 != 5:
-        raise NotImplementedError('h_scan covers the DNA / RNA alphabets; evaluate protein tables one h at a time')
-    head, head_fn = _head_for_eval(ar_func, table)
     hv = np.asarray(h.cpu() if isinstance(h, torch.Tensor) else h, dtype=np.float64).reshape(-1)
+    if table.A1 != 5:
+        # protein: the generic (dense-tensor) evaluation, one h at a time; the head is evaluated per h as well --
+        # protein tables are short-lag and small, this route is about coverage, not speed
+        lls, ces, tot = [], [], None
+        for hk in hv:
+            use_train = ds_loc_train >= 0
+            acc = None
+            for r0, n, _ in data.batches():
+                for c0 in range(r0, r0 + n, eng.EXPLICIT_CHUNK):
+                    cn = min(eng.EXPLICIT_CHUNK, r0 + n - c0)
+                    counts = eng.dense_counts(table, c0, cn)
+                    batch = [eng.onehot_rows(table, c0, cn), counts[:, ds_loc_test, :]]
+                    if use_train:
+                        batch.append(counts[:, ds_loc_train, :])
+                    with torch.no_grad():
+                        out = _evaluation_step(batch, float(hk), ar_func, [1.0], table.A1 - 1, use_train, seed=seed)
+                    part = torch.stack([out[0].reshape(()), out[3].reshape(()), out[6].reshape(())])
+                    acc = part if acc is None else acc + part
+            acc = eng.allreduce_sum(acc).cpu()
+            lls.append(acc[0])
+            ces.append(acc[1])
+            tot = acc[2]
+        ll_ear, ce = torch.stack(lls), torch.stack(ces)
+        return ll_ear, torch.exp(-ll_ear / tot), ce / tot
+    head, head_fn = _head_for_eval(ar_func, table)
     ll_ear, _, _, ce, _, _, tot = eng.eval_loop(data, ds_loc_train, ds_loc_test, hv, [1.0], head, head_fn, seed)
     return ll_ear, torch.exp(-ll_ear / tot), ce / tot

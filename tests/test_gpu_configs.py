@@ -171,3 +171,10 @@ def test_protein_alphabet_dense_route(cuda):
         assert rel(g.numpy(), w.numpy()) <= 1e-10
     bm = dl.bmm_likelihood(data, [0.5, 2.0]).numpy()
     assert rel(bm, O.bmm_likelihood(counts.astype(np.float64), np.array([0.5, 2.0])).numpy()) <= 1e-10
+    # h_scan (bear_net.py:465-531) on a protein table: every h agrees with evaluation() at that h
+    hs = np.array([0.3 * h, h, 4.0 * h])
+    ll, perp, accu = bear_net.h_scan(data, 0, 1, 'prot', hs, ar_func, seed=-1)
+    for i, hk in enumerate(hs):
+        one = bear_net.evaluation(data, 0, 1, 'prot', float(hk), ar_func, [1.0], seed=-1)
+        assert rel(ll[i].numpy(), one[0].numpy()) <= 1e-12 and rel(perp[i].numpy(), one[3].numpy()) <= 1e-12
+        assert rel(accu[i].numpy(), one[6].numpy()) <= 1e-12
