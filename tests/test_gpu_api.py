@@ -275,6 +275,9 @@ def test_run_net_script(cuda, tmp_path):
     assert r[0] == 1 and np.allclose(r[1], ll_van)
     p2, h2, f2 = bear_net.change_scope_params(5, 4, ar_funcs.make_ar_func_linear, {}, params)
     assert np.array_equal(p2[1].cpu().numpy(), params[1])
+    # precision = float32 configs (models/train_bear_net.py:43) are accepted and computed in float64
+    r32 = train_bear_net.main(_config('bear_test.cfg', tmp_path / 'net32', general__precision='float32'))
+    assert r32[0] == 1 and np.allclose(r32[1], ll_van, rtol=1e-6)
 
 
 def test_run_ref_script(cuda, tmp_path):
