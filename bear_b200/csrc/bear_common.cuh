@@ -215,4 +215,13 @@ static __device__ __noinline__ double rng_normal(uint64_t seed, uint64_t a, uint
     return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
 }
 
+// standard normal for the argmax tie-breaking noise only (Box-Muller on two 24-bit uniforms in float32 with the fast
+// intrinsics: the noise decides near-ties, its law needs no more than that; |n| <= 5.9).  Samplers use rng_normal.
+static __device__ __noinline__ double rng_normal_fast(uint64_t seed, uint64_t a, uint64_t b) {
+    const uint64_t x = rng_u64(seed, a, b);
+    const float u1 = (float(uint32_t(x >> 40)) + 0.5f) * (1.0f / 16777216.0f);
+    const float u2 = (float(uint32_t(x >> 8) & 0xffffffu) + 0.5f) * (1.0f / 16777216.0f);
+    return double(sqrtf(-2.0f * __logf(u1)) * __cosf(6.2831853071795865f * u2));
+}
+
 }  // namespace bear

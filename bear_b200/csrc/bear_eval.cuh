@@ -55,10 +55,13 @@ __device__ __forceinline__ uint32_t pick5(const uint32_t (&c)[A1], int idx) {
     return idx == 0 ? c[0] : idx == 1 ? c[1] : idx == 2 ? c[2] : idx == 3 ? c[3] : c[4];
 }
 
-// argmax of v + sigma * N(0,1) (core.py:69-71,134-136).  Candidates are the entries within 16 sigma of
-// the maximum (anything further cannot win, P < 1e-28).  One candidate: no randomness needed.  All
-// candidates exactly tied: a uniform pick, which is what iid noise gives.  Otherwise Gaussian noise on
-// the candidates only.  seed < 0: no noise, first maximum wins.
+// argmax of v + sigma * N(0,1) (core.py:69-71,134-136).  Candidates are the entries within 8 sigma of the maximum (the
+// noise lifts anything further over the maximum with probability Phi(-8 / sqrt 2) < 1e-8, and only the few per cent of
+// rows whose runner-up lies between 8 and 16 sigma would even be exposed to that).  One candidate: no randomness
+// needed.  All candidates exactly tied: a uniform pick, which is what iid noise gives.  Two candidates: the difference
+// of their noises is one N(0, 2 sigma^2) draw.  Otherwise Gaussian noise on the candidates only.  seed < 0: no noise,
+// first maximum wins.  (With small weights a few per cent of rows have a near-tie, i.e. most warps visit the slow path
+// once per tile: its cost is visible -- 10 % of the evaluation kernel on the bench's table before these two cuts.)
 struct V5 {
     double v[A1];
 };
@@ -80,10 +83,20 @@ __device__ __noinline__ int argmax_tiebreak(V5 x, double top, double thr, bool a
             }
         return best;
     }
+    int ia = -1, ib = -1, ncand = 0;
+    for (int b = 0; b < A1; ++b)
+        if (x.v[b] > thr) {
+            if (ncand == 0) ia = b; else ib = b;
+            ++ncand;
+        }
+    if (ncand == 2) {        // v_a + s n_a > v_b + s n_b  <=>  (v_a - v_b) + s sqrt(2) n > 0 with a single standard normal n
+        const double n = rng_normal_fast(uint64_t(seed), row, model * 64);
+        return (x.v[ia] - x.v[ib]) + 1.4142135623730951 * sigma * n > 0.0 ? ia : ib;
+    }
     double nb = -INFINITY;
     for (int b = 0; b < A1; ++b)
         if (x.v[b] > thr) {
-            const double y = x.v[b] + sigma * rng_normal(uint64_t(seed), row, model * 64 + uint64_t(b));
+            const double y = x.v[b] + sigma * rng_normal_fast(uint64_t(seed), row, model * 64 + uint64_t(b));
             if (y > nb) {
                 nb = y;
                 best = b;
@@ -103,7 +116,7 @@ __device__ __forceinline__ int noisy_argmax5(const double (&v)[A1], double sigma
             best = b;
         }
     if (seed < 0) return best;
-    const double thr = top - 16.0 * sigma;
+    const double thr = top - 8.0 * sigma;
     int near = 0, exact = 0;
 #pragma unroll
     for (int b = 0; b < A1; ++b) {

@@ -395,6 +395,38 @@ def test_evaluation_noise_only_moves_ties(cuda):
     assert abs(float(a[6]) - float(b[6])) < 1e-3
 
 
+def test_near_tie_noise_has_the_gaussian_law(cuda):
+    """argmax(v + sigma N(0,1)) on rows whose two best entries differ by a fraction of sigma (core.py:134-136, AR model:
+    sigma = eps): the better entry wins with probability Phi(gap / (sigma sqrt 2)); a third entry within the window is
+    handled by the general path.  Entries further than 8 sigma away never win."""
+    from scipy.stats import norm
+    from bear_b200 import _lib
+    from bear_b200._lib import lib, check, ptr
+    n, eps = 400000, 1e-7
+    dev = torch.device('cuda', 0)
+    stride = n
+    counts = torch.zeros((1, 5, stride), dtype=torch.int32, device=dev)
+    counts[0, 0] = 1                                         # every row: one transition to letter 0
+    ws = torch.empty(lib.bear_workspace_doubles(n, 1, 0), dtype=torch.float64, device=dev)
+    h = torch.ones(1, dtype=torch.float64, device=dev)
+    van = torch.ones(1, dtype=torch.float64, device=dev)
+    for gap, third, want in ((0.5 * eps, 0.0, norm.cdf(0.5 / np.sqrt(2))), (1.5 * eps, 0.0, norm.cdf(1.5 / np.sqrt(2))),
+                             (20 * eps, 0.0, 1.0), (0.5 * eps, 1.0, None)):
+        f = torch.zeros((n, 5), dtype=torch.float64, device=dev)
+        f[:, 0], f[:, 1] = 0.4, 0.4 - gap
+        f[:, 2] = 0.4 - gap if third else 0.1                # third: a three-way near tie (general path)
+        f[:, 3] = 1.0 - f[:, :3].sum(1)
+        acc = torch.zeros(7, dtype=torch.float64, device=dev)
+        check(lib.bear_eval_step(None, ptr(counts), None, stride, 0, n, 1, _lib.HEAD_EXPLICIT, ptr(f), ptr(h), 1, ptr(van), 1,
+                                 11, 0, ptr(acc), ptr(ws), _lib.stream()))
+        frac = float(acc[4]) / n                             # [ll_ear, ll_arm, ll_van, cor_ear, cor_arm, cor_van, total]
+        if want is None:
+            # P(x0 + d is the largest of three), x1 = x2 shifted down by d = 0.5 sigma: by simulation of the same law
+            z = np.random.default_rng(0).normal(size=(2000000, 3))
+            want = np.mean((z[:, 0] + 0.5 > z[:, 1]) & (z[:, 0] + 0.5 > z[:, 2]))
+        assert abs(frac - want) < 4e-3, (gap, third, frac, want)
+
+
 def test_h_scan_matches_evaluation(cuda):
     from bear_b200 import ar_funcs, bear_net, dataloader as dl
     data = dl.dataloader(YSD1, 'dna', 400, 3)
