@@ -67,8 +67,9 @@ for lag, regime, name in ((20, 0, 'lag20'), (20, 2, 'lag20-sorted'), (13, 0, 'la
             dbg(buf)
             out.append('%s issuer: %.0f cycles per product in the loop, %.0f of them issuing; %.2f sweeps per product (%.2f empty)' % (
                 name, buf[0] / max(buf[4], 1), buf[1] / max(buf[4], 1), buf[2] / max(buf[4], 1), buf[3] / max(buf[4], 1)))
-            out.append('%s producer, cycles per tile: %.0f waiting for the input stage, %.0f waiting for the slab, %.0f writing operands, %.0f in the proxy fence' % (
-                name, buf[3] / max(buf[4], 1), buf[5] / max(buf[4], 1), buf[7] / max(buf[4], 1), buf[6] / max(buf[4], 1)))
+            if buf[5]:       # (pipeline wait counters: only in the tools/experiments/train_mbarrier_issuer.patch build)
+                out.append('%s producer, cycles per tile: %.0f waiting for the input stage, %.0f waiting for the slab, %.0f writing operands, %.0f in the proxy fence' % (
+                    name, buf[3] / max(buf[4], 1), buf[5] / max(buf[4], 1), buf[7] / max(buf[4], 1), buf[6] / max(buf[4], 1)))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(5):
