@@ -2,6 +2,7 @@
 // tensors, the generic distributions of core.py, and the posterior sampler of log_gamma.py.
 #include <math.h>
 
+#include "bear_rank.h"
 #include "bear_b200.h"
 #include "bear_common.cuh"
 #include "bear_host.h"
@@ -322,8 +323,23 @@ __global__ void synth_table_kernel(uint64_t* __restrict__ kmers, uint32_t* __res
 // compact transfer format -> packed table (include/bear_b200.h).  Four rows per thread: one 32-bit load per byte
 // plane, 128-bit stores of the count planes.
 // ---------------------------------------------------------------------------------------------
+// rank -> count vector, 4 bits (A1 = 5, counts <= 10) or 2 bits (A1 = 21, counts <= 3) per letter; rebuilt before every
+// expansion that needs it (a few microseconds, stateless, identical values whoever writes them)
+__device__ uint64_t g_rank_lut[4096];
+
+__global__ void rank_lut_kernel(int A1, uint32_t nvec) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nvec) return;
+    uint8_t c[21];
+    bear_rank::unrank(r, A1, c);
+    const int cb = A1 == 5 ? 4 : 2;
+    uint64_t p = 0;
+    for (int b = 0; b < A1; ++b) p |= uint64_t(c[b]) << (cb * b);
+    g_rank_lut[r] = p;
+}
+
 __global__ void expand_table_kernel(const uint8_t* __restrict__ comp, int64_t pitch, int64_t n, int kb, int kbits_dna_lag,
-                                    int nplanes, int count_bits, uint64_t* __restrict__ kmers,
+                                    int nplanes, int A1r, int count_bits, uint64_t* __restrict__ kmers,
                                     uint32_t* __restrict__ counts, int64_t stride, bool vec) {
     const int64_t q = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;       // rows 4q .. 4q+3
     const int64_t i0 = q * 4;
@@ -343,6 +359,35 @@ __global__ void expand_table_kernel(const uint8_t* __restrict__ comp, int64_t pi
         if (i0 + j < n) kmers[i0 + j] = v[j];
     }
     const uint8_t* cplanes = comp + int64_t(kb) * pitch;
+    if (count_bits == 12) {             // 12-bit rank of the count vector of a (row, group): byte plane + nibble plane per group
+        const int G = nplanes / A1r;
+        for (int g = 0; g < G; ++g) {
+            const uint8_t* lo8 = cplanes + int64_t(g) * (pitch + pitch / 2);
+            const uint32_t wl = __ldg(reinterpret_cast<const uint32_t*>(lo8) + q);
+            const uint32_t wh = __ldg(reinterpret_cast<const uint16_t*>(lo8 + pitch) + q);
+            uint64_t packed[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t r = ((wl >> (8 * j)) & 0xffu) | (((wh >> (4 * j)) & 0xfu) << 8);
+                packed[j] = r == bear_rank::ESCAPE ? 0ull : g_rank_lut[r];      // escaped rows: zeros, patched by the escapes
+            }
+            const int cb = A1r == 5 ? 4 : 2;                                    // bits per count in a table entry
+            for (int b = 0; b < A1r; ++b) {
+                uint32_t c[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) c[j] = uint32_t(packed[j] >> (cb * b)) & ((1u << cb) - 1u);
+                uint32_t* dst = counts + int64_t(g * A1r + b) * stride + i0;
+                if (vec && i0 + 3 < n) {
+                    *reinterpret_cast<uint4*>(dst) = make_uint4(c[0], c[1], c[2], c[3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (i0 + j < n) dst[j] = c[j];
+                }
+            }
+        }
+        return;
+    }
     const int64_t cpitch = pitch * count_bits / 8;
     for (int pl = 0; pl < nplanes; ++pl) {
         uint32_t c[4];
@@ -519,7 +564,7 @@ extern "C" int bear_expand_table(const uint8_t* d_compact, const uint32_t* d_esc
     const int a = bear_alphabet_size(alphabet);
     const int count_bits = wire & 15;
     const bool start_esc = (wire & BEAR_WIRE_START_ESC) != 0;
-    BEAR_REQUIRE(a > 0 && lag >= 1 && lag <= bear_max_lag(alphabet) && G >= 1 && (count_bits == 4 || count_bits == 8), fn);
+    BEAR_REQUIRE(a > 0 && lag >= 1 && lag <= bear_max_lag(alphabet) && G >= 1 && (count_bits == 4 || count_bits == 8 || count_bits == 12), fn);
     BEAR_REQUIRE((wire & ~(15 | BEAR_WIRE_START_ESC)) == 0 && !(start_esc && alphabet == BEAR_ALPHABET_PROT), fn);
     BEAR_REQUIRE(n >= 0 && n_esc >= 0 && dst_row0 >= 0 && stride >= dst_row0 + n, fn);
     if (n == 0) return BEAR_OK;
@@ -529,8 +574,13 @@ extern "C" int bear_expand_table(const uint8_t* d_compact, const uint32_t* d_esc
     const int64_t pitch = (n + 15) / 16 * 16;
     const int64_t quads = (n + 3) / 4;
     const bool vec = (dst_row0 & 3) == 0 && (stride & 3) == 0 && (reinterpret_cast<uintptr_t>(d_counts) & 15) == 0;
+    if (count_bits == 12) {
+        const uint32_t nvec = bear_rank::num_vectors(a + 1, bear_rank::nmax(a + 1));
+        rank_lut_kernel<<<(nvec + THREADS - 1) / THREADS, THREADS, 0, ST(stream)>>>(a + 1, nvec);
+        BEAR_LAUNCH_CHECK("rank_lut_kernel");
+    }
     expand_table_kernel<<<unsigned((quads + THREADS - 1) / THREADS), THREADS, 0, ST(stream)>>>(
-        d_compact, pitch, n, kb, dna ? lag : 0, G * (a + 1), count_bits, d_kmers + dst_row0, d_counts + dst_row0, stride, vec);
+        d_compact, pitch, n, kb, dna ? lag : 0, G * (a + 1), a + 1, count_bits, d_kmers + dst_row0, d_counts + dst_row0, stride, vec);
     BEAR_LAUNCH_CHECK("expand_table_kernel");
     if (n_esc > 0) {
         expand_escapes_kernel<<<unsigned((n_esc + THREADS - 1) / THREADS), THREADS, 0, ST(stream)>>>(

@@ -20,6 +20,7 @@
 
 #include "bear_b200.h"
 #include "bear_host.h"
+#include "bear_rank.h"
 
 static thread_local char g_err[512] = "";
 
@@ -578,7 +579,7 @@ static inline int compact_kbits(int lag, int alphabet, int wire = 0) {
 }
 static inline bool wire_ok(int wire, int alphabet) {
     const int bits = wire & 15;
-    if (bits != 4 && bits != 8) return false;
+    if (bits != 4 && bits != 8 && bits != 12) return false;
     if (wire & ~(15 | BEAR_WIRE_START_ESC)) return false;
     return !(wire & BEAR_WIRE_START_ESC) || alphabet != BEAR_ALPHABET_PROT;
 }
@@ -599,6 +600,7 @@ extern "C" int64_t bear_compact_bytes(int64_t n, int lag, int alphabet, int G, i
     if (!wire_ok(wire, alphabet)) return -1;
     const int kb = (compact_kbits(lag, alphabet, wire) + 7) / 8;
     const int64_t pitch = compact_pitch(n);
+    if ((wire & 15) == 12) return pitch * kb + (pitch + pitch / 2) * int64_t(G);      // a byte + a nibble plane per group
     return pitch * kb + (pitch * (wire & 15) / 8) * int64_t(G) * (a + 1);
 }
 
@@ -636,6 +638,38 @@ extern "C" int bear_compact_choose_wire(const uint64_t* h_kmers, const uint32_t*
     }
     const int64_t bytes8 = n * nplanes + 12 * e255, bytes4 = n * nplanes / 2 + 12 * e15;
     int wire = bytes4 < bytes8 ? 4 : 8;
+    // 12-bit rank of the whole count vector of a (row, group): rows whose counts sum to more than nmax escape, one entry
+    // per non-zero count
+    {
+        const int A1 = a + 1, nmx = bear_rank::nmax(A1);
+        std::vector<int64_t> esc12(nthreads, 0);
+        std::vector<std::thread> pool2;
+        for (int t = 0; t < nthreads; ++t) {
+            pool2.emplace_back([&, t]() {
+                const int64_t lo = n * t / nthreads, hi = n * (t + 1) / nthreads;
+                int64_t e = 0;
+                for (int g = 0; g < G; ++g) {
+                    const uint32_t* src = h_counts + int64_t(g) * A1 * stride + row0;
+                    for (int64_t i = lo; i < hi; ++i) {
+                        uint64_t sum = 0;
+                        int nz = 0;
+                        for (int b = 0; b < A1; ++b) {
+                            const uint32_t c = src[int64_t(b) * stride + i];
+                            sum += c;
+                            nz += c != 0u;
+                        }
+                        if (sum > uint64_t(nmx)) e += nz;
+                    }
+                }
+                esc12[t] = e;
+            });
+        }
+        for (auto& th : pool2) th.join();
+        int64_t e12 = 0;
+        for (int t = 0; t < nthreads; ++t) e12 += esc12[t];
+        const int64_t bytes12 = n * G * 3 / 2 + 12 * e12;
+        if (bytes12 < (wire == 4 ? bytes4 : bytes8)) wire = 12;
+    }
     // start-run lengths as escapes: pays when it saves a k-mer plane and few rows are start-padded
     if (alphabet != BEAR_ALPHABET_PROT) {
         const int planes_saved = (compact_kbits(lag, alphabet, 0) + 7) / 8 - (compact_kbits(lag, alphabet, BEAR_WIRE_START_ESC) + 7) / 8;
@@ -668,6 +702,12 @@ extern "C" int bear_compact_table(const uint64_t* h_kmers, const uint32_t* h_cou
     const int64_t cpitch = pitch * count_bits / 8;      // bytes per count plane
     const uint32_t marker = count_bits == 4 ? 15u : 255u;
     const int nthreads = pack_threads(n);
+    const int nmx = bear_rank::nmax(A1);
+    // tables for the rank coding: comp[p][m] = vectors of p entries with sum m; off[N] = vectors with sum below N
+    uint32_t comp[22][12] = {}, off[13] = {};
+    for (int p2 = 1; p2 <= A1 && p2 < 22; ++p2)
+        for (int m = 0; m <= nmx && m < 12; ++m) comp[p2][m] = bear_rank::compositions(m, p2);
+    for (int N = 1; N <= nmx + 1 && N < 13; ++N) off[N] = off[N - 1] + comp[A1][N - 1];
     // k-mer planes: rows split over threads (start-run escapes per thread, i.e. ordered by row)
     std::vector<std::vector<uint32_t>> kesc(nthreads);
     {
@@ -697,8 +737,57 @@ extern "C" int bear_compact_table(const uint64_t* h_kmers, const uint32_t* h_cou
         for (auto& th : pool) th.join();
     }
     // count planes: one plane at a time per thread (keeps the escapes ordered by plane, row)
-    std::vector<std::vector<uint32_t>> esc(nplanes);
-    {
+    std::vector<std::vector<uint32_t>> esc(count_bits == 12 ? nthreads : nplanes);
+    if (count_bits == 12) {
+        // rank coding: per group a byte plane (low 8 bits of the rank) and a nibble plane (high 4 bits); rows are split
+        // over the threads at even row indices (two rows share a nibble-plane byte)
+        uint8_t* base = h_out + int64_t(kb) * pitch;
+        memset(base, 0, size_t((pitch + pitch / 2) * int64_t(G)));
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nthreads; ++t) {
+            pool.emplace_back([&, t]() {
+                const int64_t lo = (n * t / nthreads) & ~int64_t(1), hi = t == nthreads - 1 ? n : ((n * (t + 1) / nthreads) & ~int64_t(1));
+                for (int g = 0; g < G; ++g) {
+                    const uint32_t* src = h_counts + int64_t(g) * A1 * stride + row0;
+                    uint8_t* lo8 = base + int64_t(g) * (pitch + pitch / 2);
+                    uint8_t* hi4 = lo8 + pitch;
+                    for (int64_t i = lo; i < hi; ++i) {
+                        uint32_t r = bear_rank::ESCAPE, N = 0;
+                        {
+                            bool ok = true;
+                            for (int b = 0; b < A1; ++b) {
+                                const uint32_t c = src[int64_t(b) * stride + i];
+                                ok = ok && c <= uint32_t(nmx);
+                                N += ok ? c : 0u;
+                            }
+                            if (ok && N <= uint32_t(nmx)) {
+                                r = off[N];
+                                int rem = int(N);
+                                for (int b = 0; b + 1 < A1 && rem > 0; ++b) {
+                                    const int cb = int(src[int64_t(b) * stride + i]);
+                                    for (int v = 0; v < cb; ++v) r += comp[A1 - 1 - b][rem - v];
+                                    rem -= cb;
+                                }
+                            }
+                        }
+                        if (r == bear_rank::ESCAPE) {
+                            for (int b = 0; b < A1; ++b) {
+                                const uint32_t c = src[int64_t(b) * stride + i];
+                                if (c != 0u) {
+                                    esc[t].push_back(uint32_t(g * A1 + b));
+                                    esc[t].push_back(uint32_t(i));
+                                    esc[t].push_back(c);
+                                }
+                            }
+                        }
+                        lo8[i] = uint8_t(r);
+                        hi4[i >> 1] |= uint8_t((r >> 8) << (4 * (i & 1)));
+                    }
+                }
+            });
+        }
+        for (auto& th : pool) th.join();
+    } else {
         std::vector<std::thread> pool;
         for (int t = 0; t < nthreads; ++t) {
             pool.emplace_back([&, t]() {
@@ -725,14 +814,14 @@ extern "C" int bear_compact_table(const uint64_t* h_kmers, const uint32_t* h_cou
         for (auto& th : pool) th.join();
     }
     int64_t total = 0;
-    for (int pl = 0; pl < nplanes; ++pl) total += int64_t(esc[pl].size() / 3);
+    for (const auto& e : esc) total += int64_t(e.size() / 3);
     for (int t = 0; t < nthreads; ++t) total += int64_t(kesc[t].size() / 3);
     *n_esc_out = total;
     if (total > esc_cap) return BEAR_OK;              // caller re-calls with room for *n_esc_out entries
     int64_t o = 0;
-    for (int pl = 0; pl < nplanes; ++pl) {
-        if (!esc[pl].empty()) memcpy(h_esc + o * 3, esc[pl].data(), esc[pl].size() * sizeof(uint32_t));
-        o += int64_t(esc[pl].size() / 3);
+    for (const auto& e : esc) {
+        if (!e.empty()) memcpy(h_esc + o * 3, e.data(), e.size() * sizeof(uint32_t));
+        o += int64_t(e.size() / 3);
     }
     for (int t = 0; t < nthreads; ++t) {                 // start-run lengths after the count escapes
         if (!kesc[t].empty()) memcpy(h_esc + o * 3, kesc[t].data(), kesc[t].size() * sizeof(uint32_t));

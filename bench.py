@@ -603,7 +603,7 @@ def leg_e2e(c, args, model, kmers, counts, n):
     for lo, hi in zip(bounds[:-1], bounds[1:]):
         m = hi - lo
         t0 = time.perf_counter()
-        bits = lib.bear_compact_choose_wire(ptr(hk), ptr(hc), e_stride, lo, m, LAG, 0, 1)   # 4-bit counts, start runs as escapes
+        bits = lib.bear_compact_choose_wire(ptr(hk), ptr(hc), e_stride, lo, m, LAG, 0, 1)   # 12-bit count-vector ranks, start runs as escapes
         check(bits)
         nbytes = lib.bear_compact_bytes(m, LAG, 0, 1, bits)
         hb = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
@@ -688,8 +688,9 @@ def leg_e2e(c, args, model, kmers, counts, n):
     ceiling_rows = e_rows * world / copy_s           # rows/s if a step were nothing but its H2D copy
     return {'value': 2.0 * e_rows * world / e_dt, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
             'd2h_bytes_per_step': out_host.numel() * 8, 'rows_per_gpu_per_step': e_rows,
-            'host_format': 'compact transfer format (k-mer byte planes, %d-bit count planes, escapes%s), %.1f B/row'
-                           % (chunks[0][7] & 15, ' incl. start-run lengths' if chunks[0][7] & 16 else '', h2d / e_rows),
+            'host_format': 'compact transfer format (k-mer byte planes, %s, escapes%s), %.1f B/row'
+                           % ('12-bit rank of each count vector' if chunks[0][7] & 15 == 12 else '%d-bit count planes' % (chunks[0][7] & 15),
+                              ' incl. start-run lengths' if chunks[0][7] & 16 else '', h2d / e_rows),
             'h2d_ceiling': {'all_ranks_concurrent_gbs_per_rank': per_rank_gbs, 'aggregate_gbs': per_rank_gbs * world,
                             'step_if_copy_only_rows_per_s': 2.0 * ceiling_rows,
                             'e2e_frac_of_copy_only': (2.0 * e_rows * world / e_dt) / (2.0 * ceiling_rows)},

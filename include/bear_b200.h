@@ -105,7 +105,10 @@ int bear_decode_kmers(const uint64_t* h_kmers, int64_t n, int lag, int alphabet,
  * the 6 bits hold n_start --, 5*lag for protein) and one byte plane per count column and letter; a count
  * >= 255 is stored as 255 plus an escape entry {plane, row, value}.  Lossless for any table.
  * `wire` selects the variant: wire & 15 = bits per count, 8 or 4 (4: two rows per byte, low nibble = even row; a
- * count >= 15 is stored as 15 plus an escape); wire & BEAR_WIRE_START_ESC (DNA/RNA): the k-mer planes hold the 2*lag
+ * count >= 15 is stored as 15 plus an escape), or 12: ONE 12-bit code per (row, group) -- the rank of the row's whole
+ * count vector among the vectors whose counts sum to at most 10 (DNA/RNA, 3003 vectors; protein: sum <= 3), low byte in a
+ * byte plane and high nibble in a nibble plane per group; rows with larger sums carry code 4095 and send their non-zero
+ * counts as escapes (1.5 B per row and group instead of 2.5 B for the five nibble planes); wire & BEAR_WIRE_START_ESC (DNA/RNA): the k-mer planes hold the 2*lag
  * payload bits only and n_start of the start-padded rows travels as escape entries {0xffffffff, row, n_start} after
  * the count escapes -- one plane less at lag 20.  7.6 instead of 11 B per row for a one-column DNA table at lag 20
  * with sparse counts and 1 % start-padded rows.  bear_compact_choose_wire (host) scans the rows and returns the

@@ -244,6 +244,17 @@ def test_multithreaded_pack_equals_single_thread(tmp_path, monkeypatch):
         dl.KmerTable.from_file(bad, 'dna', 2)
 
 
+def _rank_vectors(A1, nmax):
+    """All count vectors of A1 entries with sum <= nmax in the order of the 12-bit rank coding (include/bear_b200.h):
+    by sum, lexicographic within one sum."""
+    def comps(m, parts):
+        if parts == 1:
+            return [[m]]
+        return [[v] + rest for v in range(m + 1) for rest in comps(m - v, parts - 1)]
+    out = [c for m in range(nmax + 1) for c in comps(m, A1)]
+    return np.array(out, dtype=np.uint32)
+
+
 def _decode_compact(buf, esc, n, lag, alphabet, G, A1, wire=8):
     """numpy reader of the compact transfer format (include/bear_b200.h)."""
     bits, start_esc = wire & 15, bool(wire & 16)
@@ -256,6 +267,28 @@ def _decode_compact(buf, esc, n, lag, alphabet, G, A1, wire=8):
     if alphabet != 'prot':
         pay = v & np.uint64((1 << (2 * lag)) - 1)
         v = pay | ((v >> np.uint64(2 * lag)) << np.uint64(58))
+    if bits == 12:                      # 12-bit rank of the (row, group) count vector: byte plane + nibble plane per group
+        nmax = 10 if A1 == 5 else 3
+        vecs = _rank_vectors(A1, nmax)
+        counts = np.zeros((G * A1, n), dtype=np.uint32)
+        escaped = np.zeros((G, n), dtype=bool)
+        for g in range(G):
+            base = kb * pitch + g * (pitch + pitch // 2)
+            lo8 = b[base:base + n].astype(np.uint32)
+            nib = b[base + pitch:base + pitch + pitch // 2].astype(np.uint32)
+            hi4 = np.stack([nib & 15, nib >> 4], axis=1).reshape(-1)[:n]
+            r = lo8 | (hi4 << 8)
+            escaped[g] = r == 4095
+            assert np.all((r < len(vecs)) | escaped[g])
+            counts[g * A1:(g + 1) * A1, ~escaped[g]] = vecs[r[~escaped[g]]].T
+        for pl, row, val in esc.numpy().view(np.uint32).reshape(-1, 3):
+            if pl == 0xffffffff:
+                assert start_esc and v[row] >> np.uint64(58) == 0
+                v[row] |= np.uint64(val) << np.uint64(58)
+                continue
+            assert escaped[pl // A1, row] and counts[pl, row] == 0 and val != 0
+            counts[pl, row] = val
+        return v, counts.reshape(G, A1, n)
     if bits == 8:
         counts = np.stack([b[(kb + pl) * pitch:(kb + pl) * pitch + n].astype(np.uint32) for pl in range(G * A1)])
     else:                               # two rows per byte, low nibble = even row
@@ -290,23 +323,31 @@ def test_compact_transfer_format_is_lossless(alphabet, lag, n, monkeypatch):
             codes[i] &= np.uint64((1 << (2 * (lag - int(ns[i])))) - 1)
         codes |= ns << np.uint64(58)
     counts = rng.integers(0, 4, size=(n, G, A1)) * rng.choice([1, 80, 85, 127, 128, 1000, 1431655765], size=(n, G, A1))
+    sparse_rows = rng.random(n) < 0.6              # rows the 12-bit rank coding can hold (small sums) next to rows it escapes
+    counts[sparse_rows] = (rng.random((int(sparse_rows.sum()), G, A1)) < 0.25) * rng.integers(1, 4, size=(int(sparse_rows.sum()), G, A1))
     table = dl.KmerTable.from_arrays((codes, lag), counts, alphabet)
     for threads in ('1', '4'):
         monkeypatch.setenv('BEAR_PACK_THREADS', threads)
         for r0, m in ((0, n), (3, n - 7), (n // 2, 1)):
             sub, ksub = table.counts_host[:, :, r0:r0 + m], table.kmers_host[r0:r0 + m]
             padded = 0 if alphabet == 'prot' else int((ksub >> np.uint64(58) != 0).sum())
-            for wire in (8, 4) + (() if alphabet == 'prot' else (8 | 16, 4 | 16)):
+            nmax = 10 if A1 == 5 else 3
+            big_rows = sub.astype(np.uint64).sum(axis=1) > nmax                      # [G, m]: rows the rank coding escapes
+            esc12 = int(((sub != 0) & big_rows[:, None, :]).sum())
+            for wire in (8, 4, 12) + (() if alphabet == 'prot' else (8 | 16, 4 | 16, 12 | 16)):
                 buf, esc, got = table.compact_chunk(r0, m, wire=wire)
                 assert got == wire and buf.numel() == table.compact_bytes(m, wire)
                 k, c = _decode_compact(buf, esc, m, lag, alphabet, G, A1, wire)
                 assert np.array_equal(k, ksub)
                 assert np.array_equal(c, sub)
-                assert esc.shape[0] == int((sub >= (255 if wire & 15 == 8 else 15)).sum()) + (padded if wire & 16 else 0)
+                want_esc = esc12 if wire & 15 == 12 else int((sub >= (255 if wire & 15 == 8 else 15)).sum())
+                assert esc.shape[0] == want_esc + (padded if wire & 16 else 0)
             # the chooser takes the variant with the fewest bytes on the wire, escapes (12 B each) included
             bytes8 = sub.size + 12 * int((sub >= 255).sum())
             bytes4 = sub.size // 2 + 12 * int((sub >= 15).sum())
             want = 4 if bytes4 < bytes8 else 8
+            if m * G * 3 // 2 + 12 * esc12 < min(bytes4, bytes8):
+                want = 12
             if alphabet != 'prot':
                 saved = (2 * lag + 6 + 7) // 8 - (2 * lag + 7) // 8
                 if saved > 0 and 12 * padded < m * saved:

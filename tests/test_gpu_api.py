@@ -354,7 +354,7 @@ def test_upload_through_compact_format_is_bit_exact(cuda, alphabet, lag, n):
     # expansion at an unaligned destination (scalar stores)
     m = min(n, 1001)
     # 4-bit count planes: every count >= 15 travels as an escape; | 16: so do the start-run lengths (DNA / RNA)
-    for bits in (8, 4) + (() if alphabet == 'prot' else (8 | 16, 4 | 16)):
+    for bits in (8, 4, 12) + (() if alphabet == 'prot' else (8 | 16, 4 | 16, 12 | 16)):
         buf, esc, got_bits = table.compact_chunk(n - m, m, wire=bits)
         assert got_bits == bits and buf.numel() == table.compact_bytes(m, bits)
         k2 = torch.zeros(m + 8, dtype=torch.int64, device=cuda)
@@ -365,15 +365,16 @@ def test_upload_through_compact_format_is_bit_exact(cuda, alphabet, lag, n):
         assert np.array_equal(k2[3:3 + m].cpu().numpy().view(np.uint64), table.kmers_host[n - m:n])
         assert np.array_equal(c2[:, :, 3:3 + m].cpu().numpy().view(np.uint32), table.counts_host[:, :, n - m:n])
         assert int(c2[:, :, :3].abs().sum()) == 0 and int(c2[:, :, 3 + m:].abs().sum()) == 0
-    # sparse counts (the benchmark regime) choose the 4-bit planes, and the upload through them is bit exact
+    # sparse counts (the benchmark regime) choose the 12-bit rank coding (protein, 21 letters of Poisson(0.6): the 4-bit
+    # planes), and the upload through them is bit exact
     small = rng.poisson(0.6, size=(n, 3, A1)) * (rng.random((n, 3, A1)) < 0.999) + 40 * (rng.random((n, 3, A1)) < 0.001)
     sparse = dl.KmerTable.from_arrays((codes, lag), small, alphabet)
-    assert sparse.compact_chunk(0, n)[2] & 15 == 4 and table.compact_chunk(0, n)[2] & 15 == 8
+    assert sparse.compact_chunk(0, n)[2] & 15 == (4 if alphabet == 'prot' else 12) and table.compact_chunk(0, n)[2] & 15 == 8
     if alphabet == 'dna' and lag == 20:     # 1 % start-padded rows: the start-run lengths travel as escapes, 5 k-mer planes
         few = codes.copy()
         few[100:] &= np.uint64((1 << 58) - 1)
         t2 = dl.KmerTable.from_arrays((few, lag), small, alphabet)
-        assert t2.compact_chunk(0, n)[2] == 4 | 16
+        assert t2.compact_chunk(0, n)[2] == 12 | 16
         k4, c4 = t2.device_tensors()
         assert np.array_equal(k4.cpu().numpy().view(np.uint64), t2.kmers_host)
         assert np.array_equal(c4.cpu().numpy().view(np.uint32), t2.counts_host)
