@@ -213,7 +213,7 @@ bmm_kernel(const uint32_t* __restrict__ counts, int64_t stride, int64_t row_lo, 
     __syncthreads();
     // Sparse rows (every count <= 8, total <= 16; the rule in k-mer tables of whole genomes): the likelihood is a linear
     // function of the HISTOGRAM of the counts -- sum_rows sum_b T_k[c_b] = sum_c hist[c] T_k[c] -- whatever the priors, so
-    // a row only bumps integer histogram bins: 8-bit fields of 64-bit registers (counts 1..8, totals 1..16), spilled
+    // a row only bumps integer histogram bins: 7- / 8-bit fields of 64-bit registers (counts 0..8, totals 1..16), spilled
     // into per-lane 32-bit bins before a field can overflow.  No table look-ups, no float arithmetic per row; the bins
     // meet the tables once, at the end.  Integer bins also make the result independent of the order of the rows.
     uint64_t hl = 0, ht0 = 0, ht1 = 0;                     // packed fields: letters with count f + 1, totals f + 1 / f + 9
@@ -226,7 +226,7 @@ bmm_kernel(const uint32_t* __restrict__ counts, int64_t stride, int64_t row_lo, 
     auto spill_fields = [&]() {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            bin_l[j] += uint32_t(hl >> (8 * j)) & 0xffu;
+            bin_l[j] += uint32_t(hl >> (7 * (j + 1))) & 0x7fu;     // (field 0 counts the zero letters: never read)
             bin_t[j] += uint32_t(ht0 >> (8 * j)) & 0xffu;
             bin_t[8 + j] += uint32_t(ht1 >> (8 * j)) & 0xffu;
         }
@@ -242,9 +242,9 @@ bmm_kernel(const uint32_t* __restrict__ counts, int64_t stride, int64_t row_lo, 
         }
         if (cmax == 0) return;
         if (NA1 == 5 && cmax <= 8u && toti <= 16u) {
+            // nine 7-bit fields, field c = letters with count c (c = 0 included: no test, no predicate per letter)
 #pragma unroll
-            for (int b = 0; b < NA1; ++b)
-                if (c[b] != 0u) hl += 1ull << (8u * (c[b] - 1u));
+            for (int b = 0; b < NA1; ++b) hl += 1ull << (7u * c[b]);
             if (toti <= 8u) ht0 += 1ull << (8u * (toti - 1u));
             else ht1 += 1ull << (8u * (toti - 9u));
         } else if (toti < uint32_t(TABN)) {
@@ -356,7 +356,7 @@ bmm_kernel(const uint32_t* __restrict__ counts, int64_t stride, int64_t row_lo, 
             row_term(cc[j]);
         }
         pending += RPL;
-        if (pending > 255 / NA1 - RPL) spill_fields();     // a field grows by at most NA1 per row
+        if (pending > 127 / NA1 - RPL) spill_fields();     // a (7-bit) field grows by at most NA1 per row
     }
     spill_fields();
 #pragma unroll
