@@ -24,7 +24,7 @@ OBJ = os.path.join(HERE, '_build')
 
 SOURCES = ['bear_pack.cpp', 'bear_dense.cu', 'bear_fused.cu', 'bear_eval_misc.cu', 'bear_eval_lin.cu', 'bear_eval_ref.cu',
            'bear_train.cu', 'bear_heads.cu', 'bear_count.cu', 'bear_cnn.cu']
-HEADERS = ['bear_common.cuh', 'bear_dm_row.cuh', 'bear_host.h', 'bear_linear_head.cuh', 'bear_sm100.cuh', 'bear_eval.cuh']
+HEADERS = ['bear_common.cuh', 'bear_dm_row.cuh', 'bear_host.h', 'bear_linear_head.cuh', 'bear_sm100.cuh', 'bear_eval.cuh', 'bear_rank.h']
 
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a',
