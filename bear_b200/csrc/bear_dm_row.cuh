@@ -172,44 +172,6 @@ __device__ __forceinline__ void letters_term(const TS* __restrict__ stir, const 
     }
 }
 
-// Evaluation, one h: the BEAR letters term  prod_b prod_{i < c_b} (conc_b + i)  and the AR term  prod_b p_b^{c_b}  in ONE
-// predicated loop over the warp's largest count (the same predicate serves both models; no coefficient table, no
-// squaring ladder).  Two partial products per model keep the multiply chains short.  Counts above SMALLC: the general
-// routines, as in letters_term / mn_term.
-__device__ __forceinline__ void letters_and_mn_terms(const double (&conc)[A1], const double (&p)[A1], const Counts& r, uint32_t steps,
-                                                     double& add_b, double& prod_b, double& add_a, double& prod_a) {
-    double b0 = 1.0, b1 = 1.0, a0 = 1.0, a1 = 1.0, kd = 0.0;
-    for (uint32_t k = 0; k < steps; ++k, kd += 1.0) {
-#pragma unroll
-        for (int b = 0; b < A1; ++b) {
-            const double t = conc[b] + kd;
-            if (r.c[b] > k) {
-                if (b & 1) {
-                    b1 *= t;
-                    a1 *= p[b];
-                } else {
-                    b0 *= t;
-                    a0 *= p[b];
-                }
-            }
-        }
-    }
-    add_b = add_a = 0.0;
-    prod_b = b0 * b1;
-    prod_a = a0 * a1;
-    if (r.cmax > SMALLC) {
-        LogProd acc;
-        prod_a = 1.0;
-#pragma unroll
-        for (int b = 0; b < A1; ++b) {
-            acc.push(lgdg_diff<false>(conc[b], double(r.c[b])));
-            if (r.c[b] != 0) add_a = fma(double(r.c[b]), log(p[b]), add_a);
-        }
-        add_b = acc.add;
-        prod_b = acc.mul;
-    }
-}
-
 // lgamma(s + n) - lgamma(s) = add + log(prod), digamma difference dg
 template <bool GRAD>
 __device__ __forceinline__ void total_term(double s, const Counts& r, double& add, double& prod, double& dg) {

@@ -406,9 +406,6 @@ eval_tile_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict_
         const bool use_tab = !HAS_TRAIN && r.n < double(TABN);
         double dummy[A1];
         uint64_t van_hash = 0;
-#ifdef BEAR_EVAL_MERGED
-        double arm_add_row = 0.0, arm_prod_row = 1.0;     // AR term of the row, evaluated together with the BEAR letters term
-#endif
         // BEAR: conc = f / h + train + eps   (bear_net.py:43, 335-337)
 #pragma unroll
         for (int k = 0; k < NH; ++k) {
@@ -416,14 +413,6 @@ eval_tile_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict_
                 double conc[A1], add, prod;
 #pragma unroll
                 for (int b = 0; b < A1; ++b) conc[b] = fma(f[b], hinv[k], tr[b]) + BEAR_EPS;
-#ifdef BEAR_EVAL_MERGED
-                if (NH == 1) {
-                    double pa[A1];
-#pragma unroll
-                    for (int b = 0; b < A1; ++b) pa[b] = f[b] + BEAR_EPS;
-                    letters_and_mn_terms(conc, pa, r, steps, add, prod, arm_add_row, arm_prod_row);
-                } else
-#endif
                 letters_term<false>(stir, conc, r, steps, add, prod, dummy);
                 if (TOT_TAB && use_tab) {
                     add -= tab_ear[k * TABN + int(r.n)];
@@ -448,12 +437,6 @@ eval_tile_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict_
             double p[A1], add, prod;
 #pragma unroll
             for (int b = 0; b < A1; ++b) p[b] = f[b] + BEAR_EPS;
-#ifdef BEAR_EVAL_MERGED
-            if (NH == 1 && H == 1) {
-                add = arm_add_row;
-                prod = arm_prod_row;
-            } else
-#endif
             mn_term(p, r, add, prod);
             if (live) {
                 arm_add += add;
