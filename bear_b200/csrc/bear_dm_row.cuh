@@ -53,6 +53,22 @@ static __constant__ double kStirling[(SMALLC + 1) * (SMALLC + 1)] = {
     0, 720, 1764, 1624, 735, 175, 21, 1, 0,
     0, 5040, 13068, 13132, 6769, 1960, 322, 28, 1};
 
+// One step of the rising factorial P and its derivative D for a lane whose count may already be used up:
+//     active (c > k):  D = D t + P;  P = P t        inactive:  P unchanged, D = D + P
+// i.e. the inactive lanes multiply by exactly 1.0.  nvcc / ptxas turn the obvious `if (c > k) {...}` (also when written as
+// predicated PTX) into both products followed by FOUR selects per step and letter -- half of the loop's instructions;
+// selecting the factor instead costs two, and the surplus D picked up over the m = steps - c inactive steps, m P, is
+// taken off once per letter after the loop (rf_fix).  P is bit-identical to the predicated form; D carries at most
+// m <= 8 extra roundings (relative 1e-15: the gradient tolerance is 1e-8).
+__device__ __forceinline__ void rf_step(uint32_t c, uint32_t k, double t, double& P, double& D) {
+    const double f = c > k ? t : 1.0;
+    D = fma(D, f, P);
+    P *= f;
+}
+__device__ __forceinline__ void rf_fix(uint32_t c, uint32_t steps, double P, double& D) {
+    D = c != 0u ? fma(-double(steps - min(c, steps)), P, D) : 0.0;      // (c = 0: P = 1 and D counted every step)
+}
+
 template <bool GRAD, typename TS>
 __device__ __forceinline__ void rf_letters(const TS* __restrict__ stir, const double (&a)[A1], const uint32_t (&c)[A1],
                                            uint32_t steps, double (&P)[A1], double (&D)[A1]) {
@@ -73,14 +89,10 @@ __device__ __forceinline__ void rf_letters(const TS* __restrict__ stir, const do
         if (last_small) {
             for (uint32_t k = 0; k < steps; ++k, kd += 1.0) {
 #pragma unroll
-                for (int b = 0; b < A1 - 1; ++b) {
-                    const double t = a[b] + kd;
-                    if (c[b] > k) {
-                        D[b] = fma(D[b], t, P[b]);
-                        P[b] *= t;
-                    }
-                }
+                for (int b = 0; b < A1 - 1; ++b) rf_step(c[b], k, a[b] + kd, P[b], D[b]);
             }
+#pragma unroll
+            for (int b = 0; b < A1 - 1; ++b) rf_fix(c[b], steps, P[b], D[b]);
             if (c[A1 - 1] != 0u) {
                 P[A1 - 1] = a[A1 - 1];
                 D[A1 - 1] = 1.0;
@@ -89,14 +101,10 @@ __device__ __forceinline__ void rf_letters(const TS* __restrict__ stir, const do
         }
         for (uint32_t k = 0; k < steps; ++k, kd += 1.0) {
 #pragma unroll
-            for (int b = 0; b < A1; ++b) {
-                const double t = a[b] + kd;
-                if (c[b] > k) {
-                    D[b] = fma(D[b], t, P[b]);
-                    P[b] *= t;
-                }
-            }
+            for (int b = 0; b < A1; ++b) rf_step(c[b], k, a[b] + kd, P[b], D[b]);
         }
+#pragma unroll
+        for (int b = 0; b < A1; ++b) rf_fix(c[b], steps, P[b], D[b]);
         return;
     }
     const TS* row[A1];     // TS = float (exact: coefficients <= 13132) halves the shared-memory traffic, double saves the conversion
