@@ -53,58 +53,53 @@ static __constant__ double kStirling[(SMALLC + 1) * (SMALLC + 1)] = {
     0, 720, 1764, 1624, 735, 175, 21, 1, 0,
     0, 5040, 13068, 13132, 6769, 1960, 322, 28, 1};
 
-// One step of the rising factorial P and its derivative D for a lane whose count may already be used up:
-//     active (c > k):  D = D t + P;  P = P t        inactive:  P unchanged, D = D + P
-// i.e. the inactive lanes multiply by exactly 1.0.  nvcc / ptxas turn the obvious `if (c > k) {...}` (also when written as
-// predicated PTX) into both products followed by FOUR selects per step and letter -- half of the loop's instructions;
-// selecting the factor instead costs two, and the surplus D picked up over the m = steps - c inactive steps, m P, is
-// taken off once per letter after the loop (rf_fix).  P is bit-identical to the predicated form; D carries at most
-// m <= 8 extra roundings (relative 1e-15: the gradient tolerance is 1e-8).
-__device__ __forceinline__ void rf_step(uint32_t c, uint32_t k, double t, double& P, double& D) {
-    const double f = c > k ? t : 1.0;
-    D = fma(D, f, P);
-    P *= f;
-}
-__device__ __forceinline__ void rf_fix(uint32_t c, uint32_t steps, double P, double& D) {
-    D = c != 0u ? fma(-double(steps - min(c, steps)), P, D) : 0.0;      // (c = 0: P = 1 and D counted every step)
+// Rising factorial P = prod_{i < c} (a + i) and its derivative D by a Horner-like recurrence that runs from the TOP:
+//     for k = steps-1 .. 0:   D = D (a + k) + P;   P = P (a + k) + [k == c]
+// starting from P = [c == steps], D = 0.  A lane's product starts when k reaches its own count (the injected 1.0), stays 0
+// before that, and every lane finishes together at k = 0 -- so the warp-uniform loop needs NO select of operands or
+// results: per step and letter one DADD, two DFMAs, one compare and one 32-bit select for the high word of the injected
+// constant.  (The `if (c > k) { D = D t + P; P *= t; }` form -- also when written as predicated PTX -- is compiled to both
+// products plus FOUR selects per step and letter, half of the loop's instructions.)  D is the exact derivative of the
+// same recurrence (d/da of (a + k) is 1, the injected constant does not depend on a).
+__device__ __forceinline__ double rf_inject(bool on) { return __hiloint2double(on ? 0x3ff00000 : 0, 0); }
+
+template <int NL>
+__device__ __forceinline__ void rf_horner(const double (&a)[A1], const uint32_t (&c)[A1], uint32_t steps, double (&P)[A1], double (&D)[A1]) {
+    uint32_t ce[NL];
+#pragma unroll
+    for (int b = 0; b < NL; ++b) {
+        ce[b] = min(c[b], steps);                 // (counts above the loop bound are redone by the general routine: keep them finite)
+        P[b] = rf_inject(ce[b] == steps);
+        D[b] = 0.0;
+    }
+    double kd = double(steps);
+    for (uint32_t k = steps; k-- > 0;) {
+        kd -= 1.0;
+#pragma unroll
+        for (int b = 0; b < NL; ++b) {
+            const double t = a[b] + kd;
+            D[b] = fma(D[b], t, P[b]);
+            P[b] = fma(P[b], t, rf_inject(k == ce[b]));
+        }
+    }
 }
 
 template <bool GRAD, typename TS>
 __device__ __forceinline__ void rf_letters(const TS* __restrict__ stir, const double (&a)[A1], const uint32_t (&c)[A1],
                                            uint32_t steps, double (&P)[A1], double (&D)[A1]) {
     if (GRAD) {
-        // with derivatives (training): predicated products (a)(a+1)...(a+c-1) -- no shared-memory traffic, no float -> double
-        // conversions; measured 2 % faster than the polynomial form below, which stays for the evaluation (5 % faster there)
+        // with derivatives (training): the recurrence above -- no shared-memory traffic, no float -> double conversions
         (void)stir;
-#pragma unroll
-        for (int b = 0; b < A1; ++b) {
-            P[b] = 1.0;
-            D[b] = 0.0;
-        }
         // The last letter is the stop symbol: about one transition per sequence, so its count is 0 or 1 in all but a
         // few rows.  When that holds for the whole warp (one vote) it is set directly and the loop runs over the other
-        // letters only: a fifth fewer predicated float64 slots.
-        const bool last_small = !__any_sync(0xffffffffu, c[A1 - 1] > 1u);
-        double kd = 0.0;
-        if (last_small) {
-            for (uint32_t k = 0; k < steps; ++k, kd += 1.0) {
-#pragma unroll
-                for (int b = 0; b < A1 - 1; ++b) rf_step(c[b], k, a[b] + kd, P[b], D[b]);
-            }
-#pragma unroll
-            for (int b = 0; b < A1 - 1; ++b) rf_fix(c[b], steps, P[b], D[b]);
-            if (c[A1 - 1] != 0u) {
-                P[A1 - 1] = a[A1 - 1];
-                D[A1 - 1] = 1.0;
-            }
-            return;
+        // letters only: a fifth fewer float64 slots.
+        if (!__any_sync(0xffffffffu, c[A1 - 1] > 1u)) {
+            rf_horner<A1 - 1>(a, c, steps, P, D);
+            P[A1 - 1] = c[A1 - 1] != 0u ? a[A1 - 1] : 1.0;
+            D[A1 - 1] = c[A1 - 1] != 0u ? 1.0 : 0.0;
+        } else {
+            rf_horner<A1>(a, c, steps, P, D);
         }
-        for (uint32_t k = 0; k < steps; ++k, kd += 1.0) {
-#pragma unroll
-            for (int b = 0; b < A1; ++b) rf_step(c[b], k, a[b] + kd, P[b], D[b]);
-        }
-#pragma unroll
-        for (int b = 0; b < A1; ++b) rf_fix(c[b], steps, P[b], D[b]);
         return;
     }
     const TS* row[A1];     // TS = float (exact: coefficients <= 13132) halves the shared-memory traffic, double saves the conversion
