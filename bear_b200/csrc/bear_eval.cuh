@@ -377,10 +377,11 @@ eval_tile_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict_
         }
         // ---- head ----
         double f[A1];
+        const bool any_start = LIN && __any_sync(0xffffffffu, (code >> 58) != 0ull);
         if (LIN) {
 #pragma unroll
             for (int b = 0; b < A1; ++b) f[b] = 0.2;
-            if (live) linear_head_geom<0>(R, head, code, lag, hg, nch, f);
+            if (live) linear_head_geom<0>(R, head, code, lag, hg, nch, f, any_start);
         } else {
 #pragma unroll
             for (int b = 0; b < A1; ++b)

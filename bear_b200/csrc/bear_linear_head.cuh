@@ -191,18 +191,16 @@ inline HeadGeom make_head_geom(int lag) {
 // softmax(sum_j mat[j, s_j, :]) of one k-mer as the normalised product of its chunk-table rows, with the chunk loop fully
 // unrolled over the precomputed geometry (NCH > 0: compile-time chunk count; NCH = 0: up to 8 chunks, `nch` at run time).
 // Rows are 32 bytes; the two 16-byte halves are swapped when bit 2 of the key is set (half_swizzle).
+// `any_start` (warp-uniform): some k-mer of the warp's tile is start-padded.  Start-padded rows are rare (only the first
+// lag positions of a sequence), so the usual tile takes the loop without the extended-key arithmetic -- as predicated
+// code it would issue for every row and chunk.
 template <int NCH>
 __device__ __forceinline__ void linear_head_geom(const double* R, const double* __restrict__ mat, uint64_t code, int lag,
-                                                 const HeadGeom& hg, int nch, double (&f)[A1]) {
+                                                 const HeadGeom& hg, int nch, double (&f)[A1], bool any_start = true) {
     const int ns = int(code >> 58);
     const uint64_t v5 = (code & PAYLOAD_MASK) << 5;
     double p0 = 1.0, p1 = 1.0, p2 = 1.0, p3 = 1.0;
-#pragma unroll
-    for (int ch = 0; ch < (NCH ? NCH : 8); ++ch) {
-        if (!NCH && ch >= nch) break;
-        const int rr = hg.rr[ch];
-        uint32_t q32 = uint32_t(v5 >> hg.sh[ch]) & (((1u << (2 * rr)) - 1u) << 5);     // 32 * key
-        if (ns > hg.c0[ch]) q32 = uint32_t(ext_key(q32 >> 5, rr, ns - hg.c0[ch])) << 5;
+    auto chunk = [&](int ch, uint32_t q32) {
         const uint32_t o = q32 | ((q32 >> 3) & 16u);
         const unsigned char* row = reinterpret_cast<const unsigned char*>(R) + ch * (ENT * 32);
         const double2 a = *reinterpret_cast<const double2*>(row + o);
@@ -211,6 +209,22 @@ __device__ __forceinline__ void linear_head_geom(const double* R, const double* 
         p1 *= a.y;
         p2 *= b.x;
         p3 *= b.y;
+    };
+    if (any_start) {
+#pragma unroll
+        for (int ch = 0; ch < (NCH ? NCH : 8); ++ch) {
+            if (!NCH && ch >= nch) break;
+            const int rr = hg.rr[ch];
+            uint32_t q32 = uint32_t(v5 >> hg.sh[ch]) & (((1u << (2 * rr)) - 1u) << 5);     // 32 * key
+            if (ns > hg.c0[ch]) q32 = uint32_t(ext_key(q32 >> 5, rr, ns - hg.c0[ch])) << 5;
+            chunk(ch, q32);
+        }
+    } else {
+#pragma unroll
+        for (int ch = 0; ch < (NCH ? NCH : 8); ++ch) {
+            if (!NCH && ch >= nch) break;
+            chunk(ch, uint32_t(v5 >> hg.sh[ch]) & (((1u << (2 * hg.rr[ch])) - 1u) << 5));
+        }
     }
     const double z = 1.0 + ((p0 + p1) + (p2 + p3));
     if (z < 1e300 && z > 1e-300) {

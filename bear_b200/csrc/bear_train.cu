@@ -310,7 +310,8 @@ linear_train_tc_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __res
                 const uint64_t v = code & PAYLOAD_MASK;
                 // ---- head: product of chunk-table rows ----
                 double f[A1];
-                linear_head_geom<NCH>(R, mat, code, lag, hg, NCH, f);
+                const bool any_start = __any_sync(0xffffffffu, ns > 0);
+                linear_head_geom<NCH>(R, mat, code, lag, hg, NCH, f, any_start);
                 // ---- likelihood and its gradient with respect to the logits ----
                 double g[4], ll_row = 0.0;
                 {
@@ -402,7 +403,6 @@ linear_train_tc_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __res
                     // row 4 lag the all-rows row
                     const uint64_t vl = v << (64 - 2 * lag);
                     const uint32_t xh = uint32_t(vl >> 32), xl = uint32_t(vl);
-                    const bool any_start = __any_sync(0xffffffffu, ns > 0);
                     unsigned char* sa = smem_raw + L.slab_a + warp * SLAB_A + lane * 16;
                     auto put_group = [&](int gI, uint4 w) {
                         if (gI >= ngrp) return;
