@@ -46,14 +46,19 @@ constexpr int T3_NW = T3_THREADS / 32;
 // warps' shared-memory or float64 traffic).  One issuing warp is enough as long as its own instruction stream is short:
 // with per-lane descriptors nvcc wraps every tcgen05 instruction in an ELECT / R2UR uniformisation loop and a product cost
 // 400-480 cycles of the issuer (the bound of the kernel); with ballots and elect.sync it is a handful of uniform ALU ops.
-constexpr int T3_NPROD = T3_NW - 1;        // warps 0 .. T3_NPROD-1 compute rows, the last warp issues the tensor-core work
+#ifndef BEAR_T3_NISSUE
+#define BEAR_T3_NISSUE 1
+#endif
+constexpr int T3_NISSUE = BEAR_T3_NISSUE;  // issuing warps: issuer q serves the row pipelines w with w % T3_NISSUE == q, into its own accumulators
+constexpr int T3_NPROD = T3_NW - T3_NISSUE;   // warps 0 .. T3_NPROD-1 compute rows, the last T3_NISSUE warps issue the tensor-core work
+static_assert(T3_NISSUE == 1 || T3_NISSUE == 2 || T3_NISSUE == 4, "1, 2 or 4 issuing warps");
 constexpr int SLAB_A = 4096;               // one-hot operand of a tile: 8 groups of 16 (position, letter) rows x 32 k-mers
 constexpr int SLAB_B = 1024;               // digit operand of a tile: 2 groups of 16 digit columns x 32 k-mers
 constexpr int STAGE_BYTES = 256 + A1 * 128;   // k-mer plane + five count planes of a 32-row tile
 constexpr int MAX_STAGES = 4;
 constexpr int NCLS = 4;                    // fixed-point scale classes; scale of class c = 2^(56 - 12 c)
 constexpr int FLUSH_IT = (1 << 21) / (T3_NPROD * 32);   // iterations between accumulator read-backs (|digit sum| < 2^28)
-constexpr uint32_t TMEM_COLS = 128;        // NCLS accumulators of 32 columns
+constexpr uint32_t TMEM_COLS = 128 * T3_NISSUE;   // per issuer: NCLS accumulators of 32 columns
 constexpr uint64_t DIGIT_BIAS = 0x0080808080808080ull;
 
 struct Train3Layout {                      // offsets in bytes from the start of dynamic shared memory
@@ -76,8 +81,8 @@ __host__ __device__ constexpr Train3Layout train3_layout(int nch, int nstage) {
     L.stir = o;       o += ((STIR_N * 4 + 15) / 16) * 16;
     L.symtab = o;     o += 2 * ENT * 2;
     L.red = o;        o += 32 * 8;
-    L.bars = o;       o += (T3_NPROD + T3_NPROD * MAX_STAGES + 1) * 8;
-    L.misc = o;       o += 64;                   // [0] tmem base [1] non-finite flag [2] classes in use; +32: 32 slab status bytes
+    L.bars = o;       o += (T3_NPROD + T3_NPROD * MAX_STAGES + T3_NISSUE) * 8;
+    L.misc = o;       o += 64;                   // [0] tmem base [1] non-finite flag [2..5] classes in use per issuer; +32: 32 slab status bytes
     o = (o + 127) & ~127;
     L.ring = o;       o += T3_NPROD * nstage * STAGE_BYTES;      // last: every other offset is independent of nstage
     L.total = o;
@@ -215,7 +220,7 @@ linear_train_tc_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __res
             mbar_init(bar_empty + 8 * w, 1);
             for (int s = 0; s < MAX_STAGES; ++s) mbar_init(bar_in + 8 * (w * MAX_STAGES + s), 1);
         }
-        mbar_init(bar_done, 1);
+        for (int q = 0; q < T3_NISSUE; ++q) mbar_init(bar_done + 8 * q, 1);
         mbar_fence_init();
         for (int i = 1; i < 16; ++i) misc[i] = 0u;           // flags and slab status bytes
     }
@@ -447,7 +452,7 @@ linear_train_tc_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __res
                 tc_fence_before();
                 __syncthreads();
                 tc_fence_after();
-                flush_accumulators(tmem, misc[2], lag, acc, acc_start, ones);
+                for (int q = 0; q < T3_NISSUE; ++q) flush_accumulators(tmem + q * 128, misc[2 + q], lag, acc, acc_start, ones);
                 tc_fence_before();
                 __syncthreads();
             }
@@ -460,13 +465,21 @@ linear_train_tc_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __res
         const uint32_t idesc = umma_idesc_i8(128, 32);
         const uint64_t desc_a0 = umma_desc(smem_u32(smem_raw + L.slab_a), 128, 512);
         const uint64_t desc_b0 = umma_desc(smem_u32(smem_raw + L.slab_b), 128, 512);
-        const uint32_t status_addr = smem_u32(smem_raw + L.misc + 32) + (lane < T3_NPROD ? lane : 0);
+        const int qi = warp - T3_NPROD;                      // this issuer: lane l watches pipeline l * T3_NISSUE + qi
+        const int my_w = lane * T3_NISSUE + qi;
+        const uint32_t status_addr = smem_u32(smem_raw + L.misc + 32) + (my_w < T3_NPROD ? my_w : 0);
+        const uint32_t my_tmem = tmem + qi * 128;
+        int n_mine = 0, n_mine_last = 0;                     // pipelines served, and those of them with a tile in the last iteration
+        for (int w = qi; w < T3_NPROD; w += T3_NISSUE) {
+            ++n_mine;
+            n_mine_last += w < nlast;
+        }
         uint32_t seen = 0;                                   // lane w: last status byte of pipeline w acted upon
         for (uint32_t it0 = 0; it0 < niter; it0 += FLUSH_IT) {
             const uint32_t it1 = it0 + FLUSH_IT < niter ? it0 + FLUSH_IT : niter;
             uint32_t cls_used = 0;                          // accumulators written since the last read-back
             // products still to issue in this window (only the very last iteration can be ragged)
-            uint32_t remaining = (it1 - it0) * T3_NPROD - (it1 == niter ? uint32_t(T3_NPROD - nlast) : 0u);
+            uint32_t remaining = (it1 - it0) * n_mine - (it1 == niter ? uint32_t(n_mine - n_mine_last) : 0u);
 #ifdef BEAR_T3_EXP_NOSLAB
             remaining = 0;
 #endif
@@ -477,7 +490,7 @@ linear_train_tc_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __res
             while (remaining) {
                 uint32_t st;
                 asm volatile("ld.acquire.cta.shared.u8 %0, [%1];" : "=r"(st) : "r"(status_addr) : "memory");
-                if (lane >= T3_NPROD) st = 0u;
+                if (my_w >= T3_NPROD) st = 0u;
                 const uint32_t ready = __ballot_sync(0xffffffffu, st != seen);
 #ifdef BEAR_T3_DEBUG
                 ++d_sweeps;
@@ -499,14 +512,15 @@ linear_train_tc_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __res
                 //  row pipelines -- measured 6.2 -> 8.9 ms)
                 uint32_t m = ready;
                 while (m) {
-                    const uint32_t w = uint32_t(__ffs(int(m))) - 1u;
+                    const uint32_t l = uint32_t(__ffs(int(m))) - 1u;
                     m &= m - 1u;
-                    const uint32_t cls = ((c0 >> w) & 1u) | (((c1 >> w) & 1u) << 1);
+                    const uint32_t w = l * T3_NISSUE + qi;
+                    const uint32_t cls = ((c0 >> l) & 1u) | (((c1 >> l) & 1u) << 1);
                     if (elect_one()) {
 #ifdef BEAR_T3_EXP_NOMMA
                         mbar_arrive(bar_empty + 8 * w);      // (experiment: no tensor-core product)
 #else
-                        umma_i8(tmem + cls * 32, desc_a0 + uint64_t(w * (SLAB_A >> 4)), desc_b0 + uint64_t(w * (SLAB_B >> 4)), idesc,
+                        umma_i8(my_tmem + cls * 32, desc_a0 + uint64_t(w * (SLAB_A >> 4)), desc_b0 + uint64_t(w * (SLAB_B >> 4)), idesc,
                                 (cls_used >> cls) & 1u);
                         umma_commit(bar_empty + 8 * w);
 #endif
@@ -524,17 +538,17 @@ linear_train_tc_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __res
                 atomicAdd(&g_t3_dbg[1], d_issue);
                 atomicAdd(&g_t3_dbg[2], d_sweeps);
                 atomicAdd(&g_t3_dbg[3], d_empty);
-                atomicAdd(&g_t3_dbg[4], (unsigned long long)((it1 - it0) * T3_NPROD));
+                atomicAdd(&g_t3_dbg[4], (unsigned long long)((it1 - it0) * n_mine));
             }
 #endif
-            if (elect_one()) umma_commit(bar_done);
-            mbar_wait(bar_done, flushes & 1u);
-            if (lane == 0) misc[2] = cls_used;
+            if (elect_one()) umma_commit(bar_done + 8 * qi);
+            mbar_wait(bar_done + 8 * qi, flushes & 1u);
+            if (lane == 0) misc[2 + qi] = cls_used;
             ++flushes;
             tc_fence_before();
             __syncthreads();
             tc_fence_after();
-            flush_accumulators(tmem, misc[2], lag, acc, acc_start, ones);
+            for (int q = 0; q < T3_NISSUE; ++q) flush_accumulators(tmem + q * 128, misc[2 + q], lag, acc, acc_start, ones);
             tc_fence_before();
             __syncthreads();
         }
