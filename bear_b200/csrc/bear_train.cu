@@ -209,6 +209,14 @@ linear_train_tc_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __res
     for (int i = threadIdx.x; i < STIR_N; i += blockDim.x) stir[i] = float(kStirling[i]);
     for (int i = threadIdx.x; i < T3_NPROD * (SLAB_A + SLAB_B) / 4; i += blockDim.x)
         reinterpret_cast<uint32_t*>(smem_raw + L.slab_a)[i] = 0u;
+    // lag a multiple of 4: the last 16-row group of the one-hot operand holds no position, only the all-rows row (and
+    // three more rows like it, never read back) -- constant, written once here instead of once per tile
+    const bool const_last = (lag & 3) == 0;
+    if (const_last) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < T3_NPROD * 32; i += blockDim.x)
+            *reinterpret_cast<uint4*>(smem_raw + L.slab_a + (i >> 5) * SLAB_A + (lag >> 2) * 512 + (i & 31) * 16) = make_uint4(1u, 1u, 1u, 1u);
+    }
     if (!TRAIN_AR && threadIdx.x < TABN) {
         // the concentrations of a row sum to 1/h + 5 eps whatever its k-mer (softmax sums to 1)
         const LgDg t = lgdg_diff<true>(hinv + A1 * BEAR_EPS, double(threadIdx.x));
@@ -253,7 +261,7 @@ linear_train_tc_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __res
     uint32_t flushes = 0;
 
     if (warp < T3_NPROD) {
-        const int ngrp = lag / 4 + 1;                       // 16-row groups of the one-hot operand that carry data
+        const int ngrp = lag / 4 + (const_last ? 0 : 1);    // 16-row groups of the one-hot operand written per tile
         const uint32_t ring = smem_u32(smem_raw + L.ring) + warp * nstage * STAGE_BYTES;
         const uint32_t my_in = bar_in + 8 * warp * MAX_STAGES;
         const uint32_t n_my = niter - (warp < nlast ? 0u : 1u);      // tiles of this warp
