@@ -392,11 +392,13 @@ linear_train_tc_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __res
                 }
                 // ---- fixed-point digits of the logit gradients: scale class from the largest |g| of the tile ----
                 uint32_t hmax = 0;
+                if (!__all_sync(0xffffffffu, live)) {        // (rare: zero-count rows, rows outside the batch in an edge tile)
 #pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    if (!live) g[b] = 0.0;
-                    hmax = max(hmax, uint32_t(__double2hiint(g[b])) & 0x7fffffffu);
+                    for (int b = 0; b < 4; ++b)
+                        if (!live) g[b] = 0.0;
                 }
+#pragma unroll
+                for (int b = 0; b < 4; ++b) hmax = max(hmax, uint32_t(__double2hiint(g[b])) & 0x7fffffffu);
                 hmax = __reduce_max_sync(0xffffffffu, hmax);
                 const int ex = int(hmax >> 20) - 1023;       // floor(log2 max|g|);  |g| <= row total < 2^35 by construction
                 const int cls = ex < 6 ? 0 : ex < 18 ? 1 : ex < 30 ? 2 : 3;
