@@ -17,7 +17,7 @@ Deviation from the reference, on purpose: ``bear_ref._evaluation_step`` reads
 ``transition_counts_train = batch[3]`` (bear_ref.py:397), which in the mapped tuple
 ``(onehot, test, train, ref)`` (bear_ref.py:502-507) is the REFERENCE column, not the training one.
 No reference test pins that path; this implementation conditions on the training column, as the
-docstring of the reference says it should.
+docstring of the reference says it should; ``evaluation(..., reference_compatible=True)`` reproduces upstream.
 """
 import numpy as np
 import torch
@@ -177,13 +177,38 @@ def train(data, num_kmers, epochs, ds_loc, ds_loc_ref, alphabet, lag, make_ar_fu
 
 
 def evaluation(data, ds_loc_train, ds_loc_test, ds_loc_ref, alphabet, h, ar_func, van_reg, dtype=torch.float64,
-               seed=None):
+               seed=None, reference_compatible=False):
     """Evaluate a trained reference-based BEAR, AR and BMM model (bear_ref.py:453-539); returns the same
-    9-tuple as ``bear_net.evaluation``."""
+    9-tuple as ``bear_net.evaluation``.
+
+    ``reference_compatible=True`` reproduces the upstream quirk described in the module docstring: with
+    ``ds_loc_train >= 0`` the BEAR and BMM posteriors are conditioned on the MAPPED REFERENCE column
+    ``(ref + eps) * not_stop`` (bear_ref.py:397 reads batch[3] of the tuple built at :502-507) instead of the training
+    column -- for comparing numbers with runs of the reference.  That route goes through the generic (dense-tensor)
+    evaluation, not the fused kernel."""
     table = eng.check_dataset(data)
 
     def f_fn(c0, cn):
         return _ref_f(ar_func, table, ds_loc_ref, c0, cn, _net_values(ar_func, table, c0, cn))[0]
+
+    if reference_compatible and ds_loc_train >= 0:
+        from . import bear_net
+        not_stop = torch.ones(table.A1, dtype=torch.float64, device=_lib.device())
+        not_stop[-1] = 0.0
+        acc = None
+        for r0, n, _ in data.batches():
+            for c0 in range(r0, r0 + n, eng.EXPLICIT_CHUNK):
+                cn = min(eng.EXPLICIT_CHUNK, r0 + n - c0)
+                counts = eng.dense_counts(table, c0, cn)
+                f = f_fn(c0, cn)
+                batch = [eng.onehot_rows(table, c0, cn), counts[:, ds_loc_test, :],
+                         (counts[:, ds_loc_ref, :] + epsilon) * not_stop]
+                with torch.no_grad():
+                    out = bear_net._evaluation_step(batch, h, lambda x, f=f: f, van_reg, table.A1 - 1, True, seed=seed)
+                acc = list(out) if acc is None else [a + o for a, o in zip(acc, out)]
+        acc = [eng.allreduce_sum(a.reshape(-1)).cpu() for a in acc]
+        ll_ear, ll_arm, ll_van, ce, ca, cv, tot = acc
+        return eng.finish_evaluation(ll_ear[0], ll_arm[0], ll_van, ce[0], ca[0], cv, tot[0])
 
     hv = float(h.item() if hasattr(h, 'item') else h)
     # stop and linear nets on DNA / RNA tables: ONE fused kernel per batch (bear_ref_eval_step: Jukes-Cantor head in

@@ -79,6 +79,11 @@ def test_bear_ref_evaluation_matches_oracle(cuda):
                             torch.tensor(0.0142, dtype=torch.float64), van)
         for g, w in zip(got, want):
             assert rel_err(g.numpy(), w.numpy()) <= 1e-10
+    # reference_compatible: upstream conditions on the mapped reference column (bear_ref.py:397) -- both modes are pinned
+    got = bear_ref.evaluation(data, 0, 1, 2, 'dna', 0.0142, ar_func, van, seed=-1, reference_compatible=True)
+    want = O.evaluation([(oh, f, counts[:, 1], refc)], torch.tensor(0.0142, dtype=torch.float64), van)
+    for g, w in zip(got, want):
+        assert rel_err(g.numpy(), w.numpy()) <= 1e-10
     # train_test path ties to the BMM closed form, as tests/test_run.py:47-51 asserts for the ref script
     assert np.allclose(bear_ref.evaluation(data, -1, 0, 2, 'dna', 1.0, ar_func, van, seed=-1)[2].numpy(),
                        [-152712571.34208855, -152709051.39618367, -152745386.2824309], rtol=1e-11)
