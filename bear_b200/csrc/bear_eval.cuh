@@ -71,9 +71,11 @@ __device__ __forceinline__ uint32_t tie_hash(int64_t seed, uint64_t row, uint64_
 }
 
 // the randomised part, out of line: ties are rare except for the unconditioned BMM (handled separately)
-__device__ __noinline__ int argmax_tiebreak(V5 x, double top, double thr, bool all_exact, int exact, double sigma,
+__device__ __noinline__ int argmax_tiebreak(V5 x, double top, double thr, int near, double sigma,
                                             int64_t seed, uint64_t row, uint64_t model) {
-    int best = 0;
+    int best = 0, exact = 0;
+    for (int b = 0; b < A1; ++b) exact += x.v[b] == top;
+    const bool all_exact = near == exact;
     if (all_exact) {
         int k = int(tie_hash(seed, row, model) % uint32_t(exact));
         for (int b = 0; b < A1; ++b)
@@ -117,17 +119,14 @@ __device__ __forceinline__ int noisy_argmax5(const double (&v)[A1], double sigma
         }
     if (seed < 0) return best;
     const double thr = top - 8.0 * sigma;
-    int near = 0, exact = 0;
+    int near = 0;                       // candidates (the exact ties among them are only counted on the slow path)
 #pragma unroll
-    for (int b = 0; b < A1; ++b) {
-        near += v[b] > thr;
-        exact += v[b] == top;
-    }
+    for (int b = 0; b < A1; ++b) near += v[b] > thr;
     if (near == 1) return best;
     V5 x;
 #pragma unroll
     for (int b = 0; b < A1; ++b) x.v[b] = v[b];
-    return argmax_tiebreak(x, top, thr, near == exact, exact, sigma, seed, row, model);
+    return argmax_tiebreak(x, top, thr, near, sigma, seed, row, model);
 }
 
 
