@@ -124,6 +124,10 @@ struct LogProd {
 // Long-running variant for per-thread accumulators spanning many rows: when the running product leaves
 // [1e-40, 1e40] its binary exponent is moved into an integer (a handful of integer instructions) instead
 // of calling log(); value() = add + ex ln 2 + log(mul).
+// (out of line: the hot loops of the fused kernels are large enough for instruction fetch to show up in the stall
+//  profile, and this path -- a running product that reached zero, a subnormal or infinity -- is almost never taken)
+static __device__ __noinline__ double log_cold(double x) { return log(x); }
+
 struct LogProdLong {
     double add = 0.0, mul = 1.0;
     int ex = 0;
@@ -135,7 +139,7 @@ struct LogProdLong {
                 ex += ((hi >> 20) & 0x7ff) - 1023;
                 mul = __hiloint2double((hi & 0x800fffff) | 0x3ff00000, __double2loint(mul));
             } else {                       // zero / subnormal / inf: keep the reference's -inf / inf
-                add += log(mul);
+                add += log_cold(mul);
                 mul = 1.0;
             }
         }

@@ -209,7 +209,7 @@ __device__ __forceinline__ void mn_term(const double (&p)[A1], const Counts& r, 
         prod = 1.0;
 #pragma unroll
         for (int b = 0; b < A1; ++b)
-            if (r.c[b] != 0) add = fma(double(r.c[b]), log(p[b]), add);
+            if (r.c[b] != 0) add = fma(double(r.c[b]), log_cold(p[b]), add);
     }
 }
 
