@@ -107,13 +107,17 @@ __device__ __forceinline__ double lg_shift_large(double a, double c, double K) {
 }
 __device__ __forceinline__ double lg_shift_const(double a) { return 0.91893853320467274178 - lgamma(a); }
 
+// log() for paths that are rarely taken inside the hot loops of the fused kernels (running-product rescues, fall-backs for
+// large counts): out of line, because those loops are large enough for instruction fetch to show up in the stall profile.
+static __device__ __noinline__ double log_cold(double x) { return log(x); }
+
 // Accumulates sum_i (add_i + log mul_i) with as few log() calls as possible.
 struct LogProd {
     double add = 0.0, mul = 1.0;
     __device__ __forceinline__ void push(double a, double m) {
         add += a;
         if (mul > 1e40 || mul < 1e-40) {
-            add += log(mul);
+            add += log_cold(mul);
             mul = 1.0;
         }
         mul *= m;
@@ -124,10 +128,6 @@ struct LogProd {
 // Long-running variant for per-thread accumulators spanning many rows: when the running product leaves
 // [1e-40, 1e40] its binary exponent is moved into an integer (a handful of integer instructions) instead
 // of calling log(); value() = add + ex ln 2 + log(mul).
-// (out of line: the hot loops of the fused kernels are large enough for instruction fetch to show up in the stall
-//  profile, and this path -- a running product that reached zero, a subnormal or infinity -- is almost never taken)
-static __device__ __noinline__ double log_cold(double x) { return log(x); }
-
 struct LogProdLong {
     double add = 0.0, mul = 1.0;
     int ex = 0;
@@ -154,7 +154,7 @@ struct LogProdLong {
 __device__ __forceinline__ double logprod_diff(const LogProd& num, const LogProd& den) {
     // both |log10 mul| <= 140 by construction, so the ratio cannot overflow
     const double ratio = num.mul / den.mul;
-    return (num.add - den.add) + (ratio == 1.0 ? 0.0 : log(ratio));
+    return (num.add - den.add) + (ratio == 1.0 ? 0.0 : log_cold(ratio));
 }
 
 // digamma(x) for x > 0 (generic dense path: gradients of lgamma at real-valued arguments)

@@ -474,7 +474,7 @@ eval_tile_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict_
                     letters_term<false>(stir, conc, r, steps, add, prod, dummy);
                     const double s = ((conc[0] + conc[1]) + (conc[2] + conc[3])) + conc[4];
                     total_term<false>(s, r, tadd, tprod, tdg);
-                    if (live) van_add[k] += (add - tadd) + log(prod / tprod);
+                    if (live) van_add[k] += (add - tadd) + log(prod / tprod);        // (heldout: hot, stays inline)
                 }
                 if (live) {
                     // no conditioning column: the five concentrations are equal and the noisy argmax is a uniform

@@ -359,7 +359,7 @@ linear_train_tc_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __res
                             double tprod;
                             const double s = ((conc[0] + conc[1]) + (conc[2] + conc[3])) + conc[4];
                             total_term<true>(s, r, tadd, tprod, tdg);
-                            tadd += log(tprod);
+                            tadd += log_cold(tprod);
                         }
                         add -= tadd;
                         // d ll/d conc_b = w_b - tdg; d ll/d f_b = that / h; softmax backward:
@@ -374,7 +374,7 @@ linear_train_tc_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __res
                     }
                     if (live) {
                         if (ll_out) {
-                            ll_row = add + log(prod);
+                            ll_row = add + log_cold(prod);          // (per-row output requested: not the bench's path)
                             run[0] += ll_row;
                         } else {
                             run[0] += add;
