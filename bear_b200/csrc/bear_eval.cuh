@@ -156,6 +156,17 @@ __device__ __noinline__ double van_dense_row(CountVec<A1> cv, double rn, double 
 }
 
 
+// the same for a prior too large for the constant-a form (rare: priors >= 64 / 5): general differences, out of line
+__device__ __noinline__ double van_general_row(CountVec<A1> cv, double rn, double vk) {
+    LogProd num, den;
+    den.push(lgdg_diff<false>(double(A1) * vk, rn));
+    for (int b = 0; b < A1; ++b) num.push(lgdg_diff<false>(vk, double(cv.c[b])));
+    return logprod_diff(num, den);
+}
+
+// row-independent total term past the table, out of line (the sparse regime never gets here)
+__device__ __noinline__ double lg_shift_large_cold(double a, double c, double K) { return lg_shift_large(a, c, K); }
+
 // warps per CTA: 16 for the common call (one h, up to four priors); the eight-model variants (h_scan, many priors) keep
 // 16 + 16 running accumulators per thread and run 8 warps with up to 255 registers instead of spilling
 #ifndef BEAR_EV_WARPS
@@ -417,7 +428,7 @@ eval_tile_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict_
                 if (TOT_TAB && use_tab) {
                     add -= tab_ear[k * TABN + int(r.n)];
                 } else if (TOT_TAB && fast_ear) {
-                    add -= lg_shift_large((HEAD == BEAR_HEAD_NONE ? 0.0 : hinv[k]) + A1 * BEAR_EPS, r.n, kconst[k]);
+                    add -= lg_shift_large_cold((HEAD == BEAR_HEAD_NONE ? 0.0 : hinv[k]) + A1 * BEAR_EPS, r.n, kconst[k]);
                 } else {
                     double tadd, tprod, tdg;
                     const double s = ((conc[0] + conc[1]) + (conc[2] + conc[3])) + conc[4];
@@ -463,11 +474,10 @@ eval_tile_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict_
                         van_add[k] += van_dense_row(cv, r.n, van[k] + BEAR_EPS, tab_van + k * TABN, kconst[NM + k],
                                                     kconst[2 * NM + k]);
                     } else {
-                        LogProd num, den;
-                        den.push(lgdg_diff<false>(((conc[0] + conc[1]) + (conc[2] + conc[3])) + conc[4], r.n));
+                        CountVec<A1> cv;
 #pragma unroll
-                        for (int b = 0; b < A1; ++b) num.push(lgdg_diff<false>(conc[b], double(r.c[b])));
-                        van_add[k] += logprod_diff(num, den);
+                        for (int b = 0; b < A1; ++b) cv.c[b] = r.c[b];
+                        van_add[k] += van_general_row(cv, r.n, van[k] + BEAR_EPS);
                     }
                 } else {
                     double add, prod, tadd, tprod, tdg;
