@@ -21,8 +21,10 @@ capture() {     # capture <name> <kernel regex> <skip> <count> <command...>
 }
 capture train_tc 'linear_train_tc_kernel' 1 1 python tools/prof_train.py
 capture eval_tile 'eval_tile_kernel' 1 1 python tools/prof_train.py
+if [ -z "${LIGHT:-}" ]; then       # LIGHT=1: only the two dominant kernels (the others did not change)
 capture misc 'bmm_kernel|decode_onehot|unpack_counts' 3 3 python tools/prof_misc.py
 ONLY=cnn CNN_ROWS=262144 capture cnn 'cnn_kernel' 1 1 python tools/bench_kernels.py
+fi
 timeout 400 python tools/bench_kernels.py > $O/${R}_kernel_bench.jsonl 2> $O/${R}_kernel_bench.err
 tail -2 $O/${R}_pytest_gpu.log
 cut -c1-600 $O/${R}_bench_full_2p31rows.json
