@@ -72,6 +72,16 @@ static int sym_code(int alphabet, char ch) {
 }
 
 // Encode one k-mer of length lag; returns 0 or a negative status.
+// What a DNA / RNA k-mer with a symbol outside the alphabet does to a file load: 0 = error (default), 1 = the row is
+// marked with BEAR_INVALID_KMER and its counts are zeroed; the caller drops marked rows (dataloader.KmerTable.from_file).
+static int g_invalid_policy = 0;
+extern "C" int bear_pack_set_invalid_policy(int policy) {
+    if (policy != 0 && policy != 1) { bear_set_error("bear_pack_set_invalid_policy: policy must be 0 (error) or 1 (mark)"); return BEAR_ERR_ARG; }
+    const int old = g_invalid_policy;
+    g_invalid_policy = policy;
+    return old;
+}
+
 static int encode_one(const char* s, int lag, int alphabet, uint64_t* out) {
     if (alphabet == BEAR_ALPHABET_PROT) {
         uint64_t v = 0;
@@ -113,6 +123,10 @@ static int encode_one(const char* s, int lag, int alphabet, uint64_t* out) {
     for (int j = 0; j < lag; ++j) {
         int c = sym_code(alphabet, s[j]);
         if (c < 0) {
+            if (g_invalid_policy == 1) {
+                *out = BEAR_INVALID_KMER;
+                return 0;
+            }
             bear_set_error("symbol '%c' outside the alphabet in k-mer '%.*s'", s[j], lag, s);
             return BEAR_ERR_PARSE;
         }

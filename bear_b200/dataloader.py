@@ -72,10 +72,28 @@ class KmerTable:
         self.stride = int(counts.shape[2])
         self._dev = None
         self._sorted = None
+        self.skipped_rows = 0          # rows dropped by from_file(on_invalid='skip')
 
     # -- construction -------------------------------------------------------------------------
     @classmethod
-    def from_file(cls, file, alphabet, num_ds, sparse=False, header=None):
+    def from_file(cls, file, alphabet, num_ds, sparse=False, header=None, on_invalid='error'):
+        """``on_invalid``: what a DNA / RNA k-mer with a symbol outside the alphabet (e.g. 'N') does -- 'error' (default)
+        or 'skip': the row is dropped and counted in ``table.skipped_rows`` (the reference one-hots such symbols to
+        zero rows, core.py:162; 2-bit codes cannot hold them)."""
+        if on_invalid not in ('error', 'skip'):
+            raise ValueError("on_invalid must be 'error' or 'skip'")
+        if on_invalid == 'skip':
+            old = check(lib.bear_pack_set_invalid_policy(1))
+            try:
+                table = cls.from_file(file, alphabet, num_ds, sparse=sparse, header=header)
+            finally:
+                lib.bear_pack_set_invalid_policy(old)
+            bad = table.kmers_host[:table.num_rows] == np.uint64(0xffffffffffffffff)
+            nbad = int(bad.sum())
+            if nbad:
+                table = table.take(np.flatnonzero(~bad))
+            table.skipped_rows = nbad
+            return table
         if header is None:
             header = bool(sparse)
         path = os.fsencode(file)

@@ -86,6 +86,13 @@ int bear_pack_sparse(const char* path, int header, int alphabet, int num_ds,
                      uint64_t* h_kmers, uint32_t* h_counts, int64_t stride,
                      int64_t* rows_out, int* lag_out);
 
+/* DNA / RNA k-mers with a symbol outside the alphabet (e.g. 'N'; the reference one-hots such symbols to a row of
+ * zeros, core.py:162, 2-bit codes cannot): policy 0 (default) = bear_pack_* fail with BEAR_ERR_PARSE naming the row;
+ * policy 1 = the row's code is BEAR_INVALID_KMER and the caller drops it (dataloader.KmerTable.from_file(on_invalid=
+ * 'skip')).  Process-wide; returns the previous policy. */
+#define BEAR_INVALID_KMER 0xffffffffffffffffull
+int bear_pack_set_invalid_policy(int policy);
+
 /* Rank-sharded ingest for data-parallel training (the reference splits every global batch over the replicas inside
  * one process, bear_net.py:273; here every rank parses only its own rows): of every global batch of `batch_rows`
  * consecutive file rows, rank keeps the contiguous slice [rank * per, (rank + 1) * per), per = ceil(rows of the batch /

@@ -154,6 +154,24 @@ def test_pack_edge_inputs(tmp_path):
             dl.KmerTable.from_file(_write(tmp_path, bad, 'bad_dec.tsv'), 'dna', 1)
 
 
+def test_invalid_symbol_policy(tmp_path):
+    """DNA k-mers with a symbol outside the alphabet: an error naming the k-mer by default, dropped (and counted) with
+    on_invalid='skip'; the other rows are unchanged.  The policy does not leak into later loads."""
+    from bear_b200 import _lib, dataloader as dl
+    rows = ['ACGTA\t[[1,2,3,4,5]]', 'ACNTA\t[[9,9,9,9,9]]', '[[CGT\t[[0,0,7,0,1]]', 'NNNNN\t[[1,1,1,1,1]]', 'TTTTT\t[[5,4,3,2,1]]']
+    path = _write(tmp_path, '\n'.join(rows) + '\n', 'n.tsv')
+    with pytest.raises(_lib.BearError, match='outside the alphabet'):
+        dl.KmerTable.from_file(path, 'dna', 1)
+    t = dl.KmerTable.from_file(path, 'dna', 1, on_invalid='skip')
+    assert t.num_rows == 3 and t.skipped_rows == 2
+    assert [k.decode() for k in t.kmers_str()] == ['ACGTA', '[[CGT', 'TTTTT']
+    assert t.counts_host[0, :, :3].T.tolist() == [[1, 2, 3, 4, 5], [0, 0, 7, 0, 1], [5, 4, 3, 2, 1]]
+    with pytest.raises(_lib.BearError, match='outside the alphabet'):
+        dl.KmerTable.from_file(path, 'dna', 1)
+    clean = dl.KmerTable.from_file(YSD1, 'dna', 3, on_invalid='skip')
+    assert clean.skipped_rows == 0 and clean.num_rows == 1365
+
+
 def test_dataset_batching_and_sharding_cover_every_row_once():
     from bear_b200 import dataloader as dl
     t = dl.KmerTable.from_file(YSD1, 'dna', 3)
