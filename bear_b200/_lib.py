@@ -55,7 +55,7 @@ _SIGNATURES = {
     'bear_pack_tsv': (_i32, [_cp, _i32, _i32, _i32, _i64, _i64, _vp, _vp, _i64, _pi64, _pi32]),
     'bear_pack_sparse': (_i32, [_cp, _i32, _i32, _i32, _i64, _i64, _vp, _vp, _i64, _pi64, _pi32]),
     'bear_pack_set_invalid_policy': (_i32, [_i32]),
-    'bear_pack_shard': (_i32, [_cp, _i32, _i32, _i32, _i32, _i64, _i32, _i32, _i64, _vp, _vp, _i64, _pi64, _pi32]),
+    'bear_pack_shard': (_i32, [_cp, _i32, _i32, _i32, _i32, _i64, _i32, _i32, _i64, _i64, _i64, _vp, _vp, _i64, _pi64, _pi32]),
     'bear_encode_kmers': (_i32, [_cp, _i64, _i32, _i32, _vp]),
     'bear_decode_kmers': (_i32, [_vp, _i64, _i32, _i32, _vp]),
     'bear_compact_bytes': (_i64, [_i64, _i32, _i32, _i32, _i32]),

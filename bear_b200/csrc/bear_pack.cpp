@@ -273,7 +273,7 @@ struct PackJob {
     bool sparse;
     // rank-sharded ingest (shard_batch > 0): of every global batch of shard_batch consecutive file rows this rank keeps
     // its contiguous slice, ceil(rows of the batch / world) rows from offset rank * that (dataloader.KmerDataset.shard)
-    int64_t shard_batch = 0, total = 0;
+    int64_t shard_batch = 0, total = 0, row_offset = 0;     // row_offset: index of the file's first row in the whole dataset
     int world = 1, rank = 0;
 
     // rows of batch b (of n_b rows) owned by the rank
@@ -282,17 +282,29 @@ struct PackJob {
         const int64_t lo = std::min<int64_t>(int64_t(rank) * per, n_b), hi = std::min<int64_t>(int64_t(rank + 1) * per, n_b);
         return hi - lo;
     }
+    // rows of the rank among dataset rows [0, g)
+    int64_t rank_rows_before(int64_t g) const {
+        const int64_t b = g / shard_batch, i = g - b * shard_batch;
+        const int64_t n_b = std::min<int64_t>(shard_batch, total - b * shard_batch);
+        int64_t in_b = 0;
+        if (n_b > 0) {
+            const int64_t per = (n_b + world - 1) / world;
+            in_b = std::min<int64_t>(std::max<int64_t>(i - int64_t(rank) * per, 0), local_rows_of(n_b));
+        }
+        return b * local_rows_of(shard_batch) + in_b;                                       // batches before b are full
+    }
     // output row of file row g, or -1 when the row belongs to another rank / lies outside the window
     int64_t out_row_of(int64_t g) const {
         if (shard_batch <= 0) {
             const int64_t o = g - first_row;
             return (o >= 0 && o < max_rows) ? o : -1;
         }
+        g += row_offset;                                                                    // index in the whole dataset
         const int64_t b = g / shard_batch, i = g - b * shard_batch;
         const int64_t n_b = std::min<int64_t>(shard_batch, total - b * shard_batch);
         const int64_t per = (n_b + world - 1) / world;
         if (i / per != rank) return -1;
-        const int64_t o = b * local_rows_of(shard_batch) + (i - int64_t(rank) * per);       // batches before b are full
+        const int64_t o = rank_rows_before(g) - rank_rows_before(row_offset);
         return o < max_rows ? o : -1;
     }
 };
@@ -460,7 +472,7 @@ const char* skip_header(const char* b, const char* e, int header) {
 
 int pack_file(const char* fn, const char* path, int header, int alphabet, int num_ds, int64_t first_row, int64_t max_rows,
               uint64_t* h_kmers, uint32_t* h_counts, int64_t stride, int64_t* rows_out, int* lag_out, bool sparse,
-              int64_t shard_batch = 0, int world = 1, int rank = 0) {
+              int64_t shard_batch = 0, int world = 1, int rank = 0, int64_t row_offset = 0, int64_t dataset_rows = -1) {
     if (!path || bear_alphabet_size(alphabet) < 0 || num_ds < 1 || first_row < 0 || max_rows < 0 || !h_kmers || !h_counts ||
         stride < max_rows || !rows_out || !lag_out || shard_batch < 0 || world < 1 || rank < 0 || rank >= world) {
         bear_set_error("%s: bad argument", fn);
@@ -479,9 +491,15 @@ int pack_file(const char* fn, const char* path, int header, int alphabet, int nu
     // the lag is the k-mer length of the first data row
     PackJob job{alphabet, num_ds, bear_alphabet_size(alphabet) + 1, 0, first_row, max_rows, stride, h_kmers, h_counts, sparse};
     job.shard_batch = shard_batch;
-    job.total = total;
+    job.total = dataset_rows >= 0 ? dataset_rows : total;
+    job.row_offset = row_offset;
     job.world = world;
     job.rank = rank;
+    if (shard_batch > 0 && (row_offset < 0 || row_offset + total > job.total)) {
+        bear_set_error("%s: the file's %lld rows at offset %lld do not fit a dataset of %lld rows", fn, (long long)total,
+                       (long long)row_offset, (long long)job.total);
+        return BEAR_ERR_ARG;
+    }
     for (const char* p = b; p < e;) {
         const char* le = line_end(p, e);
         if (!blank_line(p, le)) {
@@ -536,8 +554,7 @@ int pack_file(const char* fn, const char* path, int header, int alphabet, int nu
             return r.rc;
         }
     if (shard_batch > 0) {
-        const int64_t full = total / shard_batch, rest = total - full * shard_batch;
-        *rows_out = std::min(max_rows, full * job.local_rows_of(shard_batch) + (rest ? job.local_rows_of(rest) : 0));
+        *rows_out = std::min(max_rows, job.rank_rows_before(row_offset + total) - job.rank_rows_before(row_offset));
     } else {
         *rows_out = std::min(max_rows, total - first_row);
     }
@@ -574,14 +591,14 @@ extern "C" int bear_pack_sparse(const char* path, int header, int alphabet, int 
 }
 
 extern "C" int bear_pack_shard(const char* path, int sparse, int header, int alphabet, int num_ds, int64_t batch_rows,
-                               int world, int rank, int64_t max_rows, uint64_t* h_kmers, uint32_t* h_counts, int64_t stride,
-                               int64_t* rows_out, int* lag_out) {
-    if (batch_rows < 1) {
+                               int world, int rank, int64_t row_offset, int64_t dataset_rows, int64_t max_rows,
+                               uint64_t* h_kmers, uint32_t* h_counts, int64_t stride, int64_t* rows_out, int* lag_out) {
+    if (batch_rows < 1 || row_offset < 0) {
         bear_set_error("bear_pack_shard: bad argument");
         return BEAR_ERR_ARG;
     }
     return pack_file("bear_pack_shard", path, header, alphabet, num_ds, 0, max_rows, h_kmers, h_counts, stride, rows_out, lag_out,
-                     sparse != 0, batch_rows, world, rank);
+                     sparse != 0, batch_rows, world, rank, row_offset, dataset_rows);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -110,23 +110,27 @@ class KmerTable:
         return cls(kmers, counts, rows.value, max(lag.value, 1), alphabet)
 
     @classmethod
-    def from_file_shard(cls, file, alphabet, num_ds, batch_size, rank, world, sparse=False, header=None):
+    def from_file_shard(cls, file, alphabet, num_ds, batch_size, rank, world, sparse=False, header=None, row_offset=0,
+                        dataset_rows=None):
         """This rank's rows of a count file: of every global batch of ``batch_size`` consecutive rows the contiguous
         slice ``KmerDataset.shard`` would give it, parsed straight from the file -- no rank ever holds (or parses the
-        numbers of) the whole table.  Returns (table, total rows of the file)."""
+        numbers of) the whole table.  ``row_offset`` / ``dataset_rows``: the file is one of several of a dataset and
+        holds its rows [row_offset, row_offset + rows of the file) of ``dataset_rows``.  Returns (table, rows of the
+        file)."""
         if header is None:
             header = bool(sparse)
         path = os.fsencode(file)
         K = check(lib.bear_count_rows(path, int(header)))
+        total = K if dataset_rows is None else int(dataset_rows)
         A1 = ALPHABET_SIZES[alphabet] + 1
-        local = sum(n for _, n in shard_ranges(K, batch_size, rank, world)[0])
+        local = rank_rows_before(row_offset + K, total, batch_size, rank, world) - rank_rows_before(row_offset, total, batch_size, rank, world)
         stride = max(_round_up(local, 4), 4)
         kmers = np.zeros(stride, dtype=np.uint64)
         counts = np.zeros((num_ds, A1, stride), dtype=np.uint32)
         rows, lag = ctypes.c_int64(0), ctypes.c_int(0)
         check(lib.bear_pack_shard(path, int(bool(sparse)), int(header), _lib.ALPHABET_IDS[alphabet], num_ds, int(batch_size),
-                                  int(world), int(rank), local, ptr(kmers), ptr(counts), stride, ctypes.byref(rows),
-                                  ctypes.byref(lag)))
+                                  int(world), int(rank), int(row_offset), total, local, ptr(kmers), ptr(counts), stride,
+                                  ctypes.byref(rows), ctypes.byref(lag)))
         assert rows.value == local
         if local == 0 and K > 0:                 # a rank without rows still reports the table's lag (first row)
             k1, c1 = np.zeros(4, dtype=np.uint64), np.zeros((num_ds, A1, 4), dtype=np.uint32)
@@ -310,6 +314,21 @@ class KmerTable:
         return decode_kmers(host, self.lag, self.alphabet)
 
 
+def rank_rows_before(g, K, batch_size, rank, world):
+    """Rows owned by ``rank`` among rows [0, g) of a K-row dataset cut into global batches of ``batch_size`` rows
+    (the arithmetic of bear_pack_shard)."""
+    b, i = divmod(int(g), int(batch_size))
+    full_per = -(-int(batch_size) // world)
+    cnt_full = max(min((rank + 1) * full_per, batch_size) - min(rank * full_per, batch_size), 0)
+    n_b = min(batch_size, K - b * batch_size)
+    in_b = 0
+    if n_b > 0:
+        per = -(-n_b // world)
+        cnt_b = max(min((rank + 1) * per, n_b) - min(rank * per, n_b), 0)
+        in_b = min(max(i - rank * per, 0), cnt_b)
+    return b * cnt_full + in_b
+
+
 def shard_ranges(K, batch_size, rank, world):
     """How a table of K rows cut into global batches of ``batch_size`` rows spreads over ``world`` ranks: rank keeps
     the contiguous slice [rank * per, (rank + 1) * per) of every batch, per = ceil(rows of the batch / world).
@@ -443,9 +462,24 @@ def sparse_dataloader(file, alphabet, batch_size, num_ds, cache=False, header=Tr
 def load_files(files, alphabet, batch_size, num_ds, sparse=False, header=None):
     """Several files of one dataset (models/train_bear_net.py:78-86 interleaves them; here they are
     concatenated in name order into one resident table)."""
-    tables = [KmerTable.from_file(f, alphabet, num_ds, sparse=sparse, header=header) for f in sorted(files)]
+    import torch.distributed as dist
+    files = sorted(files)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        # every rank parses only its slice of every global batch of the concatenated dataset
+        rank, world = dist.get_rank(), dist.get_world_size()
+        hdr = bool(sparse) if header is None else header
+        rows = [count_rows(f, header=hdr) for f in files]
+        K, parts, off = sum(rows), [], 0
+        for f, n in zip(files, rows):
+            parts.append(KmerTable.from_file_shard(f, alphabet, num_ds, batch_size, rank, world, sparse=sparse, header=header,
+                                                   row_offset=off, dataset_rows=K)[0])
+            off += n
+        table = parts[0] if len(parts) == 1 else KmerTable.concat(parts)
+        ranges, grows, ids = shard_ranges(K, int(batch_size), rank, world)
+        return KmerDataset(table, batch_size, 1, ranges, grows, None, ids)
+    tables = [KmerTable.from_file(f, alphabet, num_ds, sparse=sparse, header=header) for f in files]
     table = tables[0] if len(tables) == 1 else KmerTable.concat(tables)
-    return _local_shard(KmerDataset(table, batch_size))
+    return KmerDataset(table, batch_size)
 
 
 def pack_files(files, out_path, alphabet, num_ds, sparse=False, header=None):

@@ -94,13 +94,15 @@ int bear_pack_sparse(const char* path, int header, int alphabet, int num_ds,
 int bear_pack_set_invalid_policy(int policy);
 
 /* Rank-sharded ingest for data-parallel training (the reference splits every global batch over the replicas inside
- * one process, bear_net.py:273; here every rank parses only its own rows): of every global batch of `batch_rows`
- * consecutive file rows, rank keeps the contiguous slice [rank * per, (rank + 1) * per), per = ceil(rows of the batch /
- * world), written densely in batch order.  sparse = 0: the dense TSV format, 1: the sparse format.  *rows_out = rows of
- * this rank (needs max_rows and stride >= that: at most ceil(batch_rows / world) * ceil(total / batch_rows)). */
+ * one process, bear_net.py:273; here every rank parses only its own rows): the dataset -- this file's rows at index
+ * `row_offset` of `dataset_rows` rows in all (several files of one dataset, models/train_bear_net.py:78-86; one file:
+ * row_offset = 0, dataset_rows = -1) -- is cut into global batches of `batch_rows` consecutive rows, and of every batch
+ * rank keeps the contiguous slice [rank * per, (rank + 1) * per), per = ceil(rows of the batch / world).  The rank's rows
+ * of THIS file are written densely in order.  sparse = 0: the dense TSV format, 1: the sparse format.  *rows_out = rows
+ * written (needs max_rows and stride >= that). */
 int bear_pack_shard(const char* path, int sparse, int header, int alphabet, int num_ds, int64_t batch_rows,
-                    int world, int rank, int64_t max_rows, uint64_t* h_kmers, uint32_t* h_counts, int64_t stride,
-                    int64_t* rows_out, int* lag_out);
+                    int world, int rank, int64_t row_offset, int64_t dataset_rows, int64_t max_rows,
+                    uint64_t* h_kmers, uint32_t* h_counts, int64_t stride, int64_t* rows_out, int* lag_out);
 
 /* n k-mer strings of length `lag`, concatenated without separators -> packed codes, and back. */
 int bear_encode_kmers(const char* h_text, int64_t n, int lag, int alphabet, uint64_t* h_kmers);

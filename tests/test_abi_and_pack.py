@@ -212,6 +212,36 @@ def test_rank_sharded_ingest_equals_shard_of_the_full_table(path, sparse, num_ds
         assert total == K
 
 
+def test_rank_sharded_ingest_of_a_multi_file_dataset(tmp_path):
+    """Several files of one dataset (models/train_bear_net.py:78-86): global batches run over the concatenated rows, file
+    boundaries fall anywhere inside them; every rank's per-file shards, concatenated, equal shard() of the whole table."""
+    from bear_b200 import dataloader as dl
+    lines = open(YSD1).read().splitlines()
+    cuts = [0, 333, 334, 1000, len(lines)]                       # (a one-row file among them)
+    files = []
+    for i in range(len(cuts) - 1):
+        files.append(_write(tmp_path, '\n'.join(lines[cuts[i]:cuts[i + 1]]) + '\n', 'part_%d.tsv' % i))
+    full = dl.KmerTable.from_file(YSD1, 'dna', 3)
+    K = full.num_rows
+    for batch, world in ((455, 3), (100, 4), (K, 2), (7, 5), (2000, 3)):
+        want_ds = dl.KmerDataset(full, batch)
+        for rank in range(world):
+            parts, off = [], 0
+            for f, n in zip(files, np.diff(cuts)):
+                t, k_file = dl.KmerTable.from_file_shard(f, 'dna', 3, batch, rank, world, row_offset=off, dataset_rows=K)
+                assert k_file == n
+                parts.append(t)
+                off += int(n)
+            got = dl.KmerTable.concat(parts)
+            want = want_ds.shard(rank, world).table
+            assert got.num_rows == want.num_rows
+            assert np.array_equal(got.kmers_host[:got.num_rows], want.kmers_host[:got.num_rows])
+            assert np.array_equal(got.counts_host[:, :, :got.num_rows], want.counts_host[:, :, :got.num_rows])
+            assert got.num_rows == dl.rank_rows_before(K, K, batch, rank, world)
+    with pytest.raises(Exception):                               # a file that does not fit the stated dataset
+        dl.KmerTable.from_file_shard(files[-1], 'dna', 3, 100, 0, 2, row_offset=1300, dataset_rows=1365)
+
+
 def test_packed_binary_cache_round_trip(tmp_path):
     """TSV -> BEARPACK shard -> memory-mapped table: bit-identical arrays and metadata."""
     from bear_b200 import dataloader as dl

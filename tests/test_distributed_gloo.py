@@ -34,6 +34,18 @@ def _run(rank, world, port, batch, acc_steps, out_path):
     calls = {'allreduce': 0}
     if world > 1:
         assert data.table.num_rows < K
+        # the same dataset split into two files goes through load_files (what the config scripts call): identical shards
+        parts = [os.path.join(os.path.dirname(out_path), 'part_%d.tsv' % i) for i in range(2)]
+        if rank == 0:
+            lines = open(YSD1).read().splitlines()
+            for path, chunk in zip(parts, (lines[:601], lines[601:])):
+                with open(path, 'w') as fh:
+                    fh.write('\n'.join(chunk) + '\n')
+        dist.barrier()
+        two = dl.load_files(parts, 'dna', batch, 3)
+        assert two.ranges == data.ranges and two.global_rows == data.global_rows and two.row_ids == data.row_ids
+        assert np.array_equal(two.table.kmers_host[:two.table.num_rows], data.table.kmers_host[:data.table.num_rows])
+        assert np.array_equal(two.table.counts_host[:, :, :two.table.num_rows], data.table.counts_host[:, :, :data.table.num_rows])
         real = dist.all_reduce
 
         def counting(t, *a, **k):
